@@ -1,0 +1,287 @@
+"""ctypes bindings used by the tests: the CPU oracle (oracle/, checker only) and the
+host-side FHE stand-in (hostfhe, keygen/encode/encrypt/decrypt -- not the hot path)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "reference-seal-backend_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+
+
+def p64(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ROOT, "oracle", "libhe_oracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+        o = C.CDLL(path)
+        o.orc_plain_modulus_batching.restype = C.c_uint64
+        o.orc_plain_modulus_batching.argtypes = [C.c_size_t, C.c_int]
+        o.orc_coeff_modulus_create.argtypes = [C.c_size_t, C.POINTER(C.c_int), C.c_size_t, u64p]
+        o.orc_minimal_primitive_root.argtypes = [C.c_uint64, C.c_uint64, u64p]
+        o.orc_get_primes.argtypes = [C.c_uint64, C.c_int, C.c_size_t, u64p]
+        o.orc_galois_elt_from_step.restype = C.c_uint32
+        o.orc_galois_elt_from_step.argtypes = [C.c_int, C.c_size_t]
+        o.orc_galois_elts_all.argtypes = [C.c_size_t, u32p]
+        o.orc_galois_table_ntt.argtypes = [C.c_size_t, C.c_uint32, u32p]
+        o.orc_ctx_create.restype = C.c_void_p
+        o.orc_ctx_create.argtypes = [C.c_int, C.c_size_t, C.c_size_t, u64p, C.c_uint64]
+        o.orc_ctx_destroy.argtypes = [C.c_void_p]
+        o.orc_ctx_psi.restype = C.c_uint64
+        o.orc_ctx_psi.argtypes = [C.c_void_p, C.c_size_t]
+        o.orc_ctx_bsk_size.restype = C.c_size_t
+        o.orc_ctx_bsk_size.argtypes = [C.c_void_p]
+        o.orc_ctx_bsk.argtypes = [C.c_void_p, u64p]
+        for f in ("orc_ntt_fwd", "orc_ntt_inv"):
+            getattr(o, f).argtypes = [C.c_void_p, C.c_size_t, u64p]
+        o.orc_ntt_fwd_direct.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p]
+        for f in ("orc_add", "orc_sub", "orc_multiply_plain", "orc_add_plain"):
+            getattr(o, f).argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, u64p, u64p]
+        o.orc_ckks_multiply.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, u64p]
+        o.orc_bfv_multiply.argtypes = [C.c_void_p, u64p, u64p, u64p]
+        o.orc_switch_key.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, u64p]
+        o.orc_relinearize.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, u64p]
+        o.orc_apply_galois.argtypes = [C.c_void_p, C.c_size_t, u64p, C.c_uint32, u64p]
+        o.orc_rotate.argtypes = [C.c_void_p, C.c_size_t, u64p, C.c_int, u32p, C.POINTER(u64p), C.c_size_t]
+        o.orc_rescale.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, u64p]
+        o.orc_mod_drop.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, u64p]
+        o.orc_batch_mul_relin_rescale.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, u64p, u64p, u64p, C.c_int]
+        o.orc_accumulate.argtypes = [C.c_void_p, C.c_size_t, u64p, C.c_size_t, u32p, C.POINTER(u64p), C.c_size_t]
+        o.orc_batch_dot.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, u64p, C.c_size_t, u64p, u32p,
+                                    C.POINTER(u64p), C.c_size_t, u64p, C.c_int]
+        o.orc_batch_ntt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, C.c_int, C.c_int]
+        _oracle = o
+    return _oracle
+
+
+_hfhe = None
+
+
+def hostfhe():
+    global _hfhe
+    if _hfhe is None:
+        h = C.CDLL(os.path.join(PKG, "hostfhe", "libhostfhe.so"))
+        h.hfhe_create.restype = C.c_void_p
+        h.hfhe_create.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_uint64]
+        h.hfhe_destroy.argtypes = [C.c_void_p]
+        for f, rt in (("hfhe_N", C.c_size_t), ("hfhe_K", C.c_size_t), ("hfhe_moduli", u64p), ("hfhe_psi", u64p),
+                      ("hfhe_plain_modulus", C.c_uint64), ("hfhe_scale", C.c_double), ("hfhe_relin_key", u64p),
+                      ("hfhe_galois_count", C.c_size_t), ("hfhe_kswitch_key_words", C.c_size_t)):
+            getattr(h, f).restype = rt
+            getattr(h, f).argtypes = [C.c_void_p]
+        h.hfhe_galois_elt.restype = C.c_uint32
+        h.hfhe_galois_elt.argtypes = [C.c_void_p, C.c_size_t]
+        h.hfhe_galois_key.restype = u64p
+        h.hfhe_galois_key.argtypes = [C.c_void_p, C.c_uint32]
+        h.hfhe_ckks_encode.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_double, u64p]
+        h.hfhe_ckks_decode.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_double, C.POINTER(C.c_double)]
+        h.hfhe_bfv_encode.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_size_t, u64p]
+        h.hfhe_bfv_decode.argtypes = [C.c_void_p, u64p, C.POINTER(C.c_int64)]
+        h.hfhe_encrypt.argtypes = [C.c_void_p, u64p, u64p]
+        h.hfhe_decrypt.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_size_t, u64p]
+        _hfhe = h
+    return _hfhe
+
+
+BFV, CKKS = 1, 2
+
+
+class Host:
+    """hostfhe context: parameter chain + keys + encode/encrypt/decrypt/decode."""
+
+    def __init__(self, scheme, N, depth, coeff_bits, sp_bits, seed=1234):
+        self.h = hostfhe()
+        self.c = self.h.hfhe_create(scheme, N, depth, coeff_bits, sp_bits, seed)
+        self.scheme, self.N, self.K, self.Ltop = scheme, N, depth + 1, depth
+        self.moduli = np.ctypeslib.as_array(self.h.hfhe_moduli(self.c), (self.K,)).copy()
+        self.psi = np.ctypeslib.as_array(self.h.hfhe_psi(self.c), (self.K,)).copy()
+        self.t = self.h.hfhe_plain_modulus(self.c)
+        self.scale = self.h.hfhe_scale(self.c)
+        self.kwords = self.h.hfhe_kswitch_key_words(self.c)
+
+    def __del__(self):
+        try:
+            self.h.hfhe_destroy(self.c)
+        except Exception:
+            pass
+
+    def relin_key(self):
+        return np.ctypeslib.as_array(self.h.hfhe_relin_key(self.c), (self.kwords,)).copy()
+
+    def galois_elts(self):
+        return [self.h.hfhe_galois_elt(self.c, i) for i in range(self.h.hfhe_galois_count(self.c))]
+
+    def galois_key(self, elt):
+        p = self.h.hfhe_galois_key(self.c, elt)
+        assert p
+        return np.ctypeslib.as_array(p, (self.kwords,)).copy()
+
+    def encode(self, vals, scale=None):
+        if self.scheme == CKKS:
+            v = np.ascontiguousarray(vals, dtype=np.float64)
+            out = np.empty(self.Ltop * self.N, dtype=np.uint64)
+            self.h.hfhe_ckks_encode(self.c, v.ctypes.data_as(C.POINTER(C.c_double)), len(v),
+                                    self.scale if scale is None else scale, p64(out))
+        else:
+            v = np.ascontiguousarray(vals, dtype=np.int64)
+            out = np.empty(self.N, dtype=np.uint64)
+            self.h.hfhe_bfv_encode(self.c, v.ctypes.data_as(C.POINTER(C.c_int64)), len(v), p64(out))
+        return out
+
+    def encrypt(self, plain):
+        ct = np.empty(2 * self.Ltop * self.N, dtype=np.uint64)
+        self.h.hfhe_encrypt(self.c, p64(plain), p64(ct))
+        return ct
+
+    def decrypt(self, ct, size, L):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        out = np.empty(L * self.N if self.scheme == CKKS else self.N, dtype=np.uint64)
+        self.h.hfhe_decrypt(self.c, p64(ct), size, L, p64(out))
+        return out
+
+    def decode(self, plain, L=None, scale=None):
+        if self.scheme == CKKS:
+            out = np.empty(self.N // 2, dtype=np.float64)
+            self.h.hfhe_ckks_decode(self.c, p64(plain), L, self.scale if scale is None else scale,
+                                    out.ctypes.data_as(C.POINTER(C.c_double)))
+        else:
+            out = np.empty(self.N, dtype=np.int64)
+            self.h.hfhe_bfv_decode(self.c, p64(plain), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
+
+    def enc_vec(self, vals):
+        return self.encrypt(self.encode(vals))
+
+    def dec_vec(self, ct, size, L, scale=None):
+        return self.decode(self.decrypt(ct, size, L), L, scale)
+
+
+class Oracle:
+    """CPU oracle context (checker)."""
+
+    def __init__(self, scheme, N, moduli, t=0):
+        self.o = oracle()
+        self.N, self.K, self.scheme = N, len(moduli), scheme
+        self.moduli = np.ascontiguousarray(moduli, dtype=np.uint64)
+        self.c = self.o.orc_ctx_create(scheme, N, self.K, p64(self.moduli), t)
+
+    def __del__(self):
+        try:
+            self.o.orc_ctx_destroy(self.c)
+        except Exception:
+            pass
+
+    def psi(self):
+        return np.array([self.o.orc_ctx_psi(self.c, i) for i in range(self.K)], dtype=np.uint64)
+
+    def ntt(self, limb, poly, inverse=False):
+        x = np.array(poly, dtype=np.uint64, copy=True)
+        (self.o.orc_ntt_inv if inverse else self.o.orc_ntt_fwd)(self.c, limb, p64(x))
+        return x
+
+    def add(self, L, size, a, b):
+        out = np.empty_like(a)
+        self.o.orc_add(self.c, L, size, p64(a), p64(b), p64(out))
+        return out
+
+    def ckks_multiply(self, L, a, b):
+        out = np.empty(3 * L * self.N, dtype=np.uint64)
+        self.o.orc_ckks_multiply(self.c, L, p64(a), p64(b), p64(out))
+        return out
+
+    def bfv_multiply(self, a, b):
+        out = np.empty(3 * (self.K - 1) * self.N, dtype=np.uint64)
+        self.o.orc_bfv_multiply(self.c, p64(a), p64(b), p64(out))
+        return out
+
+    def relinearize(self, L, ct3, key):
+        out = np.empty(2 * L * self.N, dtype=np.uint64)
+        self.o.orc_relinearize(self.c, L, p64(ct3), p64(key), p64(out))
+        return out
+
+    def switch_key(self, L, ct, target, key):
+        out = np.array(ct, dtype=np.uint64, copy=True)
+        self.o.orc_switch_key(self.c, L, p64(out), p64(target), p64(key))
+        return out
+
+    def apply_galois(self, L, ct, elt, key):
+        out = np.array(ct, dtype=np.uint64, copy=True)
+        self.o.orc_apply_galois(self.c, L, p64(out), elt, p64(key))
+        return out
+
+    @staticmethod
+    def _keyargs(keys):
+        elts = np.array(list(keys.keys()), dtype=np.uint32)
+        arr = (u64p * len(keys))(*[p64(k) for k in keys.values()])
+        return elts, arr
+
+    def rotate(self, L, ct, step, keys):
+        out = np.array(ct, dtype=np.uint64, copy=True)
+        elts, arr = self._keyargs(keys)
+        rc = self.o.orc_rotate(self.c, L, p64(out), step, elts.ctypes.data_as(u32p), arr, len(keys))
+        assert rc == 0, rc
+        return out
+
+    def accumulate(self, L, ct, count, keys):
+        out = np.array(ct, dtype=np.uint64, copy=True)
+        elts, arr = self._keyargs(keys)
+        rc = self.o.orc_accumulate(self.c, L, p64(out), count, elts.ctypes.data_as(u32p), arr, len(keys))
+        assert rc == 0, rc
+        return out
+
+    def rescale(self, L, size, ct):
+        out = np.empty(size * (L - 1) * self.N, dtype=np.uint64)
+        self.o.orc_rescale(self.c, L, size, p64(ct), p64(out))
+        return out
+
+    def mod_drop(self, L, size, ct):
+        out = np.empty(size * (L - 1) * self.N, dtype=np.uint64)
+        self.o.orc_mod_drop(self.c, L, size, p64(ct), p64(out))
+        return out
+
+    def multiply_plain(self, L, size, ct, plain):
+        out = np.empty(size * L * self.N, dtype=np.uint64)
+        self.o.orc_multiply_plain(self.c, L, size, p64(ct), p64(plain), p64(out))
+        return out
+
+    def add_plain(self, L, size, ct, plain):
+        out = np.empty(size * L * self.N, dtype=np.uint64)
+        self.o.orc_add_plain(self.c, L, size, p64(ct), p64(plain), p64(out))
+        return out
+
+    def mul_relin_rescale(self, L, n, a, b, key, threads=0):
+        out = np.empty(n * 2 * (L - 1) * self.N, dtype=np.uint64)
+        self.o.orc_batch_mul_relin_rescale(self.c, L, n, p64(a), p64(b), p64(key), p64(out), threads)
+        return out
+
+    def batch_dot(self, L, n, a, b, count, relin, keys, threads=0):
+        out = np.empty(n * 2 * L * self.N, dtype=np.uint64)
+        elts, arr = self._keyargs(keys)
+        rc = self.o.orc_batch_dot(self.c, L, n, p64(a), p64(b), count, p64(relin), elts.ctypes.data_as(u32p), arr,
+                                  len(keys), p64(out), threads)
+        assert rc == 0, rc
+        return out
+
+
+def rand_residues(rng, moduli, shape_prefix, N):
+    """uniform residues: array [*shape_prefix, len(moduli), N] with limb l in [0, moduli[l])"""
+    out = np.empty(tuple(shape_prefix) + (len(moduli), N), dtype=np.uint64)
+    for l, q in enumerate(moduli):
+        out[..., l, :] = rng.integers(0, int(q), size=tuple(shape_prefix) + (N,), dtype=np.uint64)
+    return out
