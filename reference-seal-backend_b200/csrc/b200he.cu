@@ -1,0 +1,1016 @@
+// b200he.cu -- host side of libb200he.so: the C ABI of include/b200he.h on top of the sm_100a
+// kernels in kernels.cuh.  One context = one GPU + one stream; every evaluator entry enqueues
+// kernels and returns, b200he_ctx_sync / b200he_batch_download wait.
+//
+// There is no CPU path in this file: without a CUDA device b200he_ctx_create fails.  (The same
+// source is compiled as host C++ with -DB200HE_EMU by tests/emu/ only, to check the kernels' index
+// arithmetic against the oracle in a GPU-less container; that build is test infrastructure and the
+// Python binding of the product refuses to load it.)
+#include "../../include/b200he.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hostmath.h"
+#include "kernels.cuh"
+#include "behz.cuh"
+
+#ifndef B200HE_EMU
+#define B200HE_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+using namespace b200he;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) return fail("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(call)            \
+    do {                     \
+        int rc_ = (call);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+extern "C" const char *b200he_last_error(void) { return g_err.c_str(); }
+extern "C" const char *b200he_version(void)
+{
+#ifdef B200HE_EMU
+    return "b200he EMU (test infrastructure, host C++)";
+#else
+    return "b200he sm_100a " __DATE__;
+#endif
+}
+
+// ------------------------------------------------------------------------------------ device pool
+// Stream-ordered reuse: every allocation is used on the context's single stream only, so a block
+// handed back to the pool may be given out again immediately.
+struct DevPool {
+    std::multimap<size_t, void *> free_blocks;
+    std::map<void *, size_t> sizes;
+    size_t total = 0;
+    void *get(size_t bytes)
+    {
+        bytes = (bytes + 511) / 512 * 512;
+        if (!bytes) bytes = 512;
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 4) {
+            void *p = it->second;
+            free_blocks.erase(it);
+            return p;
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            release();
+            if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        }
+        sizes[p] = bytes;
+        total += bytes;
+        return p;
+    }
+    void put(void *p)
+    {
+        if (p) free_blocks.emplace(sizes[p], p);
+    }
+    void release()
+    {
+        for (auto &kv : free_blocks) {
+            total -= kv.first;
+            sizes.erase(kv.second);
+            cudaFree(kv.second);
+        }
+        free_blocks.clear();
+    }
+};
+
+// ------------------------------------------------------------------------------------ context
+struct ProfRec {
+    int cls;
+    cudaEvent_t a, b;
+};
+
+struct b200he_ctx {
+    int scheme = 0, device = 0;
+    u32 N = 0, K = 0;
+    int logn = 0, lognl = 0, c = 0;   // N = 2^logn; CTA-local transform 2^lognl; limb split 2^c ways
+    u64 t = 0;
+    int M = 0;                        // moduli in the tables: K chain primes (+ BEHZ auxiliary primes)
+    std::vector<Mod> mods;
+    Tables T{};
+    void *d_tables = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevPool pool;
+    u64 workspace = u64(2) << 30;
+    u64 *relin = nullptr;
+    std::map<u32, u64 *> gal;
+    std::map<u32, u32 *> galtab;
+    uint64_t launches = 0;
+    bool prof = false;
+    std::vector<ProfRec> recs;
+    Behz behz{};   // BFV only
+    int nBsk = 0;
+};
+
+struct b200he_batch {
+    b200he_ctx *ctx = nullptr;
+    u64 *d = nullptr;
+    size_t cap_words = 0;
+    uint64_t count = 0;
+    int size = 0, L = 0, ntt = 0;
+    double scale = 1.0;
+    size_t ct_words() const { return (size_t)size * L * ctx->N; }
+};
+
+static inline void prof_pre(b200he_ctx *c, int cls)
+{
+    c->launches++;
+    if (c->prof) {
+        ProfRec r{ cls, nullptr, nullptr };
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c->stream);
+        c->recs.push_back(r);
+    }
+}
+static inline void prof_post(b200he_ctx *c)
+{
+    if (c->prof) cudaEventRecord(c->recs.back().b, c->stream);
+}
+#define LAUNCH(ctx, cls, kernel, grid, block, smem, ...)                          \
+    do {                                                                          \
+        prof_pre(ctx, cls);                                                       \
+        B200HE_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);     \
+        prof_post(ctx);                                                           \
+    } while (0)
+#define LAUNCH_CHECK() CK(cudaGetLastError())
+
+// dispatch on the CTA-local transform size
+#define NTT_DISPATCH(ctx, STMT)                                   \
+    switch ((ctx)->lognl) {                                       \
+    case 10: { constexpr int LG = 10; STMT; } break;              \
+    case 11: { constexpr int LG = 11; STMT; } break;              \
+    case 12: { constexpr int LG = 12; STMT; } break;              \
+    default: { constexpr int LG = 13; STMT; } break;              \
+    }
+
+static inline unsigned blocks_for(size_t threads, unsigned block = 256) { return (unsigned)((threads + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------ tables
+static Mod make_mod(u64 q, u64 N)
+{
+    Mod m{};
+    m.q = q;
+    m.two_q = 2 * q;
+    m.bits = (u32)hm::bitlen(q);
+    m.sh = m.bits - 2;
+    m.mu = (u64)((((hm::u128)1) << (62 + m.bits)) / q);
+    m.r64 = (u64)((((hm::u128)1) << 64) / q);
+    m.ninv = hm::invmod(N % q, q);
+    m.ninv_s = hm::shoup(m.ninv, q);
+    return m;
+}
+
+static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std::vector<u64> &psi)
+{
+    const size_t N = c->N, M = moduli.size();
+    c->M = (int)M;
+    c->mods.resize(M);
+    std::vector<ulonglong2> tw(M * N), itw(M * N), qinv(M * M);
+    std::vector<u64> halfmod(M * M);
+    for (size_t i = 0; i < M; i++) {
+        const u64 q = moduli[i];
+        c->mods[i] = make_mod(q, N);
+        const u64 ipsi = hm::invmod(psi[i], q);
+        u64 p = 1, ip = 1;
+        for (size_t k = 0; k < N; k++) {
+            const size_t r = hm::brv((uint32_t)k, c->logn);
+            tw[i * N + r] = make_ulonglong2(p, hm::shoup(p, q));
+            itw[i * N + r] = make_ulonglong2(ip, hm::shoup(ip, q));
+            p = hm::mulmod(p, psi[i], q);
+            ip = hm::mulmod(ip, ipsi, q);
+        }
+        // slot 0 (the unused psi^0) carries the last inverse stage's twiddle with N^{-1} folded in
+        const u64 w = hm::mulmod(itw[i * N + 1].x, c->mods[i].ninv, q);
+        itw[i * N] = make_ulonglong2(w, hm::shoup(w, q));
+        for (size_t x = 0; x < M; x++) {
+            const u64 qx = moduli[x];
+            u64 inv = (x == i) ? 0 : hm::invmod(qx % q, q);
+            qinv[x * M + i] = make_ulonglong2(inv, hm::shoup(inv, q));
+            halfmod[x * M + i] = (qx >> 1) % q;
+        }
+    }
+    const size_t b_mods = M * sizeof(Mod), b_tw = M * N * sizeof(ulonglong2), b_qinv = M * M * sizeof(ulonglong2),
+                 b_half = M * M * sizeof(u64);
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t total = al(b_mods) + 2 * al(b_tw) + al(b_qinv) + al(b_half);
+    CK(cudaMalloc(&c->d_tables, total));
+    unsigned char *p = (unsigned char *)c->d_tables;
+    CK(cudaMemcpy(p, c->mods.data(), b_mods, cudaMemcpyHostToDevice));
+    c->T.mods = (const Mod *)p;
+    p += al(b_mods);
+    CK(cudaMemcpy(p, tw.data(), b_tw, cudaMemcpyHostToDevice));
+    c->T.tw = (const ulonglong2 *)p;
+    p += al(b_tw);
+    CK(cudaMemcpy(p, itw.data(), b_tw, cudaMemcpyHostToDevice));
+    c->T.itw = (const ulonglong2 *)p;
+    p += al(b_tw);
+    CK(cudaMemcpy(p, qinv.data(), b_qinv, cudaMemcpyHostToDevice));
+    c->T.qinv = (const ulonglong2 *)p;
+    p += al(b_qinv);
+    CK(cudaMemcpy(p, halfmod.data(), b_half, cudaMemcpyHostToDevice));
+    c->T.halfmod = (const u64 *)p;
+    c->T.N = (int)N;
+    c->T.M = (int)M;
+    return 0;
+}
+
+template <int LG> static int set_smem_attrs()
+{
+#ifndef B200HE_EMU
+    const int bytes = NttCfg<LG>::SMEM_BYTES;
+    CK(cudaFuncSetAttribute(k_ntt_fwd<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_ntt_inv<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_ks_inner<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_moddown<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#endif
+    return 0;
+}
+
+static int init_behz(b200he_ctx *c, std::vector<u64> &moduli, std::vector<u64> &psi);
+static int upload_behz(b200he_ctx *c);
+
+extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint64_t *moduli, const uint64_t *psi,
+                                 uint64_t plain_modulus, int device, b200he_ctx **out)
+{
+    if (!out) return fail("ctx_create: out is NULL");
+    *out = nullptr;
+    if (scheme != B200HE_BFV && scheme != B200HE_CKKS) return fail("ctx_create: unknown scheme %d", scheme);
+    int logn = 0;
+    while ((1u << logn) < N) logn++;
+    if ((1u << logn) != N || logn < 10 || logn > 15) return fail("ctx_create: N=%u must be a power of two in [1024, 32768]", N);
+    if (K < 1 || K > 32) return fail("ctx_create: K=%u out of range", K);
+    if (!moduli || !psi) return fail("ctx_create: moduli/psi NULL");
+    std::vector<u64> mv(moduli, moduli + K), pv(psi, psi + K);
+    for (u32 i = 0; i < K; i++) {
+        if (mv[i] >> 61 || mv[i] < 3 || (mv[i] - 1) % (2 * (u64)N)) return fail("ctx_create: modulus %u (%llu) must be < 2^61 and = 1 mod 2N", i, (unsigned long long)mv[i]);
+        if (hm::powmod(pv[i], N, mv[i]) != mv[i] - 1) return fail("ctx_create: psi[%u] is not a primitive 2N-th root", i);
+        for (u32 j = 0; j < i; j++)
+            if (mv[j] == mv[i]) return fail("ctx_create: repeated modulus");
+    }
+    if (scheme == B200HE_BFV && (plain_modulus < 2 || K < 2)) return fail("ctx_create: BFV needs plain_modulus >= 2 and K >= 2");
+#ifndef B200HE_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("ctx_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail("ctx_create: device %d out of range (%d present)", device, ndev);
+#endif
+    CK(cudaSetDevice(device));
+    b200he_ctx *c = new b200he_ctx;
+    c->scheme = scheme;
+    c->device = device;
+    c->N = N;
+    c->K = K;
+    c->logn = logn;
+    c->lognl = logn > 13 ? 13 : logn;
+    c->c = logn - c->lognl;
+    c->t = plain_modulus;
+    if (scheme == B200HE_BFV && init_behz(c, mv, pv)) { delete c; return -1; }
+    if (build_tables(c, mv, pv)) { delete c; return -1; }
+    if (scheme == B200HE_BFV && upload_behz(c)) { delete c; return -1; }
+#ifndef B200HE_EMU
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("ctx_create: stream"); }
+    c->own_stream = true;
+#endif
+    int rc = 0;
+    NTT_DISPATCH(c, rc = set_smem_attrs<LG>());
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return 0;
+}
+
+extern "C" void b200he_ctx_destroy(b200he_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (c->relin) cudaFree(c->relin);
+    for (auto &kv : c->gal) cudaFree(kv.second);
+    for (auto &kv : c->galtab) cudaFree(kv.second);
+    c->pool.release();
+    for (auto &kv : c->pool.sizes) cudaFree(kv.first);   // blocks still held by undestroyed batches
+    if (c->d_tables) cudaFree(c->d_tables);
+    if (c->behz.d_blob) cudaFree(c->behz.d_blob);
+#ifndef B200HE_EMU
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+#endif
+    delete c;
+}
+
+extern "C" int b200he_ctx_set_stream(b200he_ctx *c, void *s)
+{
+    if (!c) return fail("set_stream: ctx NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+#ifndef B200HE_EMU
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+#endif
+    c->own_stream = false;
+    c->stream = (cudaStream_t)s;
+    return 0;
+}
+extern "C" int b200he_ctx_sync(b200he_ctx *c)
+{
+    if (!c) return fail("sync: ctx NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int b200he_ctx_set_workspace(b200he_ctx *c, uint64_t bytes)
+{
+    if (!c || bytes < (u64(1) << 20)) return fail("set_workspace: need >= 1 MiB");
+    c->workspace = bytes;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ keys
+static size_t key_words(const b200he_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->N; }
+
+extern "C" int b200he_set_relin_key(b200he_ctx *c, const uint64_t *key)
+{
+    if (!c || !key) return fail("set_relin_key: NULL argument");
+    if (c->K < 2) return fail("set_relin_key: context has no special prime (K < 2)");
+    CK(cudaSetDevice(c->device));
+    if (!c->relin) CK(cudaMalloc((void **)&c->relin, key_words(c) * 8));
+    CK(cudaMemcpyAsync(c->relin, key, key_words(c) * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int b200he_set_galois_key(b200he_ctx *c, uint32_t elt, const uint64_t *key)
+{
+    if (!c || !key) return fail("set_galois_key: NULL argument");
+    if (c->K < 2) return fail("set_galois_key: context has no special prime (K < 2)");
+    if (!(elt & 1) || elt >= 2 * c->N) return fail("set_galois_key: invalid Galois element %u", elt);
+    CK(cudaSetDevice(c->device));
+    u64 *&d = c->gal[elt];
+    if (!d) CK(cudaMalloc((void **)&d, key_words(c) * 8));
+    CK(cudaMemcpyAsync(d, key, key_words(c) * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int b200he_has_galois_key(const b200he_ctx *c, uint32_t elt) { return c && c->gal.count(elt) ? 1 : 0; }
+
+// NTT-form Galois permutation (SEAL GaloisTool::generate_table_ntt): out[i] = in[table[i]]
+static int galois_table(b200he_ctx *c, u32 elt, const u32 **out)
+{
+    auto it = c->galtab.find(elt);
+    if (it == c->galtab.end()) {
+        const u32 N = c->N;
+        std::vector<u32> tab(N);
+        for (u32 i = 0; i < N; i++) {
+            const u32 odd = 2 * hm::brv(i, c->logn) + 1;
+            const u32 idx = (u32)(((u64)elt * odd) & (2 * (u64)N - 1));
+            tab[i] = hm::brv((idx - 1) >> 1, c->logn);
+        }
+        u32 *d = nullptr;
+        CK(cudaMalloc((void **)&d, N * sizeof(u32)));
+        CK(cudaMemcpy(d, tab.data(), N * sizeof(u32), cudaMemcpyHostToDevice));
+        it = c->galtab.emplace(elt, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ batches
+extern "C" int b200he_batch_create(b200he_ctx *c, b200he_batch **out)
+{
+    if (!c || !out) return fail("batch_create: NULL argument");
+    b200he_batch *b = new b200he_batch;
+    b->ctx = c;
+    *out = b;
+    return 0;
+}
+extern "C" void b200he_batch_destroy(b200he_batch *b)
+{
+    if (!b) return;
+    b->ctx->pool.put(b->d);
+    delete b;
+}
+static int batch_shape(b200he_batch *b, uint64_t count, int size, int L, int ntt, double scale)
+{
+    b200he_ctx *c = b->ctx;
+    if (size < 1 || size > 3) return fail("batch: size %d out of range", size);
+    const int Lmax = c->K > 1 ? (int)c->K - 1 : 1;
+    if (L < 1 || L > Lmax) return fail("batch: level L=%d out of range [1,%d]", L, Lmax);
+    const size_t words = (size_t)count * size * L * c->N;
+    if (words > b->cap_words) {
+        CK(cudaSetDevice(c->device));
+        c->pool.put(b->d);
+        b->d = (u64 *)c->pool.get(words * 8);
+        if (!b->d) { b->cap_words = 0; return fail("batch: out of device memory (%zu bytes)", words * 8); }
+        b->cap_words = c->pool.sizes[b->d] / 8;
+    }
+    b->count = count;
+    b->size = size;
+    b->L = L;
+    b->ntt = ntt;
+    b->scale = scale;
+    return 0;
+}
+extern "C" int b200he_batch_resize(b200he_batch *b, uint64_t count, int size, int L, int ntt_form, double scale)
+{
+    if (!b) return fail("batch_resize: NULL batch");
+    return batch_shape(b, count, size, L, ntt_form, scale);
+}
+extern "C" int b200he_batch_upload(b200he_batch *b, uint64_t first, uint64_t n, const uint64_t *host)
+{
+    if (!b || !host) return fail("batch_upload: NULL argument");
+    if (first + n > b->count) return fail("batch_upload: range [%llu,%llu) exceeds count %llu", (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)b->count);
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaMemcpyAsync(b->d + first * b->ct_words(), host, n * b->ct_words() * 8, cudaMemcpyHostToDevice, b->ctx->stream));
+    return 0;
+}
+extern "C" int b200he_batch_download(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host)
+{
+    if (!b || !host) return fail("batch_download: NULL argument");
+    if (first + n > b->count) return fail("batch_download: range exceeds count");
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaMemcpyAsync(host, b->d + first * b->ct_words(), n * b->ct_words() * 8, cudaMemcpyDeviceToHost, b->ctx->stream));
+    CK(cudaStreamSynchronize(b->ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" uint64_t b200he_batch_count(const b200he_batch *b) { return b ? b->count : 0; }
+extern "C" int b200he_batch_size(const b200he_batch *b) { return b ? b->size : 0; }
+extern "C" int b200he_batch_level(const b200he_batch *b) { return b ? b->L : 0; }
+extern "C" int b200he_batch_ntt_form(const b200he_batch *b) { return b ? b->ntt : 0; }
+extern "C" double b200he_batch_scale(const b200he_batch *b) { return b ? b->scale : 0.0; }
+extern "C" int b200he_batch_set_scale(b200he_batch *b, double s)
+{
+    if (!b) return fail("batch_set_scale: NULL batch");
+    b->scale = s;
+    return 0;
+}
+extern "C" void *b200he_batch_device_ptr(b200he_batch *b) { return b ? b->d : nullptr; }
+
+// Output staging: ops write into a fresh block when the output handle aliases an input, then swap.
+struct OutBuf {
+    b200he_batch *out;
+    b200he_batch tmp;
+    bool aliased;
+    OutBuf(b200he_batch *o, const b200he_batch *a, const b200he_batch *b = nullptr) : out(o), aliased(o == a || o == b) { tmp.ctx = o->ctx; }
+    int shape(uint64_t count, int size, int L, int ntt, double scale)
+    {
+        return batch_shape(aliased ? &tmp : out, count, size, L, ntt, scale);
+    }
+    u64 *ptr() { return aliased ? tmp.d : out->d; }
+    void commit()
+    {
+        if (!aliased) return;
+        out->ctx->pool.put(out->d);
+        out->d = tmp.d;
+        out->cap_words = tmp.cap_words;
+        out->count = tmp.count;
+        out->size = tmp.size;
+        out->L = tmp.L;
+        out->ntt = tmp.ntt;
+        out->scale = tmp.scale;
+        tmp.d = nullptr;
+    }
+    ~OutBuf()
+    {
+        if (tmp.d) out->ctx->pool.put(tmp.d);
+    }
+};
+
+// device copy of a host index map (NULL stays NULL = identity); bounds-checked on the host
+struct DevIdx {
+    b200he_ctx *c;
+    u32 *d = nullptr;
+    DevIdx(b200he_ctx *c_) : c(c_) {}
+    int set(const uint32_t *host, uint64_t n, uint64_t limit, const char *what)
+    {
+        if (!host) return 0;
+        for (uint64_t i = 0; i < n; i++)
+            if (host[i] >= limit) return fail("%s: index %u at position %llu out of range (count %llu)", what, host[i], (unsigned long long)i, (unsigned long long)limit);
+        d = (u32 *)c->pool.get(n * sizeof(u32));
+        if (!d) return fail("%s: out of device memory", what);
+        CK(cudaMemcpyAsync(d, host, n * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    ~DevIdx() { c->pool.put(d); }
+};
+
+static bool same_scale(double a, double b) { return fabs(a - b) <= 1e-9 * fmax(fabs(a), fabs(b)) || a == b; }
+
+// ------------------------------------------------------------------------------------ transforms
+// forward NTT of nlimbs limbs (grouped L per outer stride).  In place only when the limb is unsplit.
+static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base)
+{
+    if (!nlimbs) return 0;
+    NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_NTT_FWD, k_ntt_fwd<LG>, (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
+                           c->T, src, dst, src_outer, dst_outer, L, mod_base, c->c));
+    LAUNCH_CHECK();
+    return 0;
+}
+static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base, int mode)
+{
+    if (!nlimbs) return 0;
+    NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_NTT_INV, k_ntt_inv<LG>, (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
+                           c->T, src, dst, src_outer, dst_outer, L, mod_base, c->c, mode));
+    LAUNCH_CHECK();
+    if (c->c > 0) {
+        const size_t threads = nlimbs * ((size_t)c->N >> c->c) / 2;
+        LAUNCH(c, B200HE_KERN_NTT_INV_TAIL, k_ntt_inv_tail, blocks_for(threads), 256, 0, c->T, dst, dst_outer, nlimbs, L, mod_base, c->c, mode);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int batch_transform(b200he_ctx *c, const b200he_batch *in, b200he_batch *out, bool inverse)
+{
+    if (!c || !in || !out) return fail("ntt: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("ntt: batch belongs to another context");
+    if ((in->ntt != 0) != inverse) return fail("ntt: input is %s NTT form", in->ntt ? "already in" : "not in");
+    CK(cudaSetDevice(c->device));
+    OutBuf ob(out, (c->c > 0 || true) ? in : nullptr);
+    TRY(ob.shape(in->count, in->size, in->L, inverse ? 0 : 1, in->scale));
+    const size_t nl = (size_t)in->count * in->size * in->L, outer = (size_t)in->L * c->N;
+    if (inverse) TRY(ntt_inv(c, in->d, ob.ptr(), nl, outer, outer, in->L, 0, INV_PLAIN));
+    else TRY(ntt_fwd(c, in->d, ob.ptr(), nl, outer, outer, in->L, 0));
+    ob.commit();
+    return 0;
+}
+extern "C" int b200he_ntt_forward(b200he_ctx *c, const b200he_batch *in, b200he_batch *out) { return batch_transform(c, in, out, false); }
+extern "C" int b200he_ntt_inverse(b200he_ctx *c, const b200he_batch *in, b200he_batch *out) { return batch_transform(c, in, out, true); }
+
+// ------------------------------------------------------------------------------------ elementwise
+static int check_pair(b200he_ctx *c, const b200he_batch *a, const b200he_batch *b, b200he_batch *out, const char *what)
+{
+    if (!c || !a || !b || !out) return fail("%s: NULL argument", what);
+    if (a->ctx != c || b->ctx != c || out->ctx != c) return fail("%s: batch belongs to another context", what);
+    if (a->L != b->L) return fail("%s: operands are at different levels (%d vs %d)", what, a->L, b->L);
+    if (a->ntt != b->ntt) return fail("%s: operands differ in NTT form", what);
+    return 0;
+}
+
+static int add_sub(b200he_ctx *c, const b200he_batch *a, const uint32_t *ai, const b200he_batch *b, const uint32_t *bi, uint64_t n,
+                   b200he_batch *out, bool sub)
+{
+    const char *what = sub ? "sub" : "add";
+    TRY(check_pair(c, a, b, out, what));
+    if (c->scheme == B200HE_CKKS && !same_scale(a->scale, b->scale)) return fail("%s: scale mismatch", what);
+    if ((!ai && n > a->count) || (!bi && n > b->count)) return fail("%s: n exceeds operand count", what);
+    CK(cudaSetDevice(c->device));
+    DevIdx da(c), db(c);
+    TRY(da.set(ai, n, a->count, what));
+    TRY(db.set(bi, n, b->count, what));
+    const int smin = a->size < b->size ? a->size : b->size, smax = a->size < b->size ? b->size : a->size;
+    OutBuf ob(out, a, b);
+    TRY(ob.shape(n, smax, a->L, a->ntt, a->scale));
+    if (!n) { ob.commit(); return 0; }
+    const size_t LN = (size_t)a->L * c->N;
+    EwArgs A{};
+    A.a = a->d; A.b = b->d; A.out = ob.ptr(); A.ai = da.d; A.bi = db.d;
+    A.a_stride = a->ct_words(); A.b_stride = b->ct_words(); A.out_stride = smax * LN;
+    A.polys = smin; A.b_polys = smin; A.L = a->L; A.mod_base = 0; A.n = n;
+    const unsigned grid = blocks_for(n * smin * LN / 2);
+    if (sub) LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_SUB>, grid, 256, 0, c->T, A);
+    else LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_ADD>, grid, 256, 0, c->T, A);
+    LAUNCH_CHECK();
+    if (smax > smin) {   // the longer operand's extra polynomials pass through (negated for b in a - b)
+        const b200he_batch *big = a->size > b->size ? a : b;
+        if (sub && big == b) return fail("sub: size(b) > size(a) is not supported");
+        CopyArgs C{};
+        C.src = big->d + smin * LN; C.dst = ob.ptr() + smin * LN; C.idx = (big == a) ? da.d : db.d;
+        C.src_stride = big->ct_words(); C.dst_stride = smax * LN; C.polys = smax - smin; C.L_in = a->L; C.L_out = a->L; C.n = n;
+        LAUNCH(c, B200HE_KERN_COPY, k_copy_limbs, blocks_for(n * (smax - smin) * LN / 2), 256, 0, c->T, C);
+        LAUNCH_CHECK();
+    }
+    ob.commit();
+    return 0;
+}
+extern "C" int b200he_add(b200he_ctx *c, const b200he_batch *a, const uint32_t *ai, const b200he_batch *b, const uint32_t *bi, uint64_t n, b200he_batch *out)
+{
+    return add_sub(c, a, ai, b, bi, n, out, false);
+}
+extern "C" int b200he_sub(b200he_ctx *c, const b200he_batch *a, const uint32_t *ai, const b200he_batch *b, const uint32_t *bi, uint64_t n, b200he_batch *out)
+{
+    return add_sub(c, a, ai, b, bi, n, out, true);
+}
+
+static int bfv_multiply(b200he_ctx *c, const b200he_batch *a, const u32 *dai, const b200he_batch *b, const u32 *dbi, uint64_t n, u64 *out);
+
+extern "C" int b200he_multiply(b200he_ctx *c, const b200he_batch *a, const uint32_t *ai, const b200he_batch *b, const uint32_t *bi, uint64_t n, b200he_batch *out)
+{
+    TRY(check_pair(c, a, b, out, "multiply"));
+    if (a->size != 2 || b->size != 2) return fail("multiply: operands must have size 2 (got %d, %d)", a->size, b->size);
+    if ((!ai && n > a->count) || (!bi && n > b->count)) return fail("multiply: n exceeds operand count");
+    CK(cudaSetDevice(c->device));
+    DevIdx da(c), db(c);
+    TRY(da.set(ai, n, a->count, "multiply"));
+    TRY(db.set(bi, n, b->count, "multiply"));
+    OutBuf ob(out, a, b);
+    if (c->scheme == B200HE_CKKS) {
+        if (!a->ntt) return fail("multiply: CKKS operands must be in NTT form");
+        TRY(ob.shape(n, 3, a->L, 1, a->scale * b->scale));
+        if (n) {
+            EwArgs A{};
+            A.a = a->d; A.b = b->d; A.out = ob.ptr(); A.ai = da.d; A.bi = db.d;
+            A.a_stride = a->ct_words(); A.b_stride = b->ct_words(); A.out_stride = 3 * (size_t)a->L * c->N;
+            A.polys = 2; A.b_polys = 2; A.L = a->L; A.mod_base = 0; A.n = n;
+            LAUNCH(c, B200HE_KERN_TENSOR, k_tensor, blocks_for(n * (size_t)a->L * c->N / 2), 256, 0, c->T, A);
+            LAUNCH_CHECK();
+        }
+    } else {
+        if (a->ntt) return fail("multiply: BFV operands must be in coefficient form");
+        if (a->L != (int)c->K - 1) return fail("multiply: BFV multiply is implemented at the top data level only (L=%d)", (int)c->K - 1);
+        TRY(ob.shape(n, 3, a->L, 0, 1.0));
+        if (n) TRY(bfv_multiply(c, a, da.d, b, db.d, n, ob.ptr()));
+    }
+    ob.commit();
+    return 0;
+}
+
+static int plain_op(b200he_ctx *c, const b200he_batch *ct, const b200he_batch *pl, const uint32_t *pi, b200he_batch *out, bool mul)
+{
+    const char *what = mul ? "multiply_plain" : "add_plain";
+    TRY(check_pair(c, ct, pl, out, what));
+    if (pl->size != 1) return fail("%s: plaintext batch must have size 1", what);
+    if (c->scheme != B200HE_CKKS || !ct->ntt) return fail("%s: implemented for CKKS (NTT form) only, as used by the reference", what);
+    if (!mul && !same_scale(ct->scale, pl->scale)) return fail("add_plain: scale mismatch");
+    const uint64_t n = ct->count;
+    std::vector<u32> bcast;
+    if (!pi && pl->count != n) {
+        if (pl->count != 1) return fail("%s: plaintext count %llu does not match ciphertext count %llu", what, (unsigned long long)pl->count, (unsigned long long)n);
+        bcast.assign(n, 0);
+        pi = bcast.data();
+    }
+    CK(cudaSetDevice(c->device));
+    DevIdx dp(c);
+    TRY(dp.set(pi, n, pl->count, what));
+    OutBuf ob(out, ct, pl);
+    TRY(ob.shape(n, ct->size, ct->L, 1, mul ? ct->scale * pl->scale : ct->scale));
+    if (n) {
+        EwArgs A{};
+        A.a = ct->d; A.b = pl->d; A.out = ob.ptr(); A.ai = nullptr; A.bi = dp.d;
+        A.a_stride = ct->ct_words(); A.b_stride = pl->ct_words(); A.out_stride = ct->ct_words();
+        A.polys = ct->size; A.b_polys = 1; A.L = ct->L; A.mod_base = 0; A.n = n;
+        const unsigned grid = blocks_for(n * ct->ct_words() / 2);
+        if (mul) LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_MUL>, grid, 256, 0, c->T, A);
+        else LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_ADD>, grid, 256, 0, c->T, A);
+        LAUNCH_CHECK();
+    }
+    ob.commit();
+    return 0;
+}
+extern "C" int b200he_multiply_plain(b200he_ctx *c, const b200he_batch *ct, const b200he_batch *pl, const uint32_t *pi, b200he_batch *out)
+{
+    return plain_op(c, ct, pl, pi, out, true);
+}
+extern "C" int b200he_add_plain(b200he_ctx *c, const b200he_batch *ct, const b200he_batch *pl, const uint32_t *pi, b200he_batch *out)
+{
+    return plain_op(c, ct, pl, pi, out, false);
+}
+
+static int copy_limbs(b200he_ctx *c, const u64 *src, size_t src_stride, u64 *dst, size_t dst_stride, const u32 *didx, uint64_t n, int polys,
+                      int L_in, int L_out)
+{
+    if (!n) return 0;
+    CopyArgs C{};
+    C.src = src; C.dst = dst; C.idx = didx; C.src_stride = src_stride; C.dst_stride = dst_stride;
+    C.polys = polys; C.L_in = L_in; C.L_out = L_out; C.n = n;
+    LAUNCH(c, B200HE_KERN_COPY, k_copy_limbs, blocks_for(n * polys * (size_t)L_out * c->N / 2), 256, 0, c->T, C);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200he_mod_drop(b200he_ctx *c, const b200he_batch *in, int L_target, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("mod_drop: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("mod_drop: batch belongs to another context");
+    if (L_target < 1 || L_target > in->L) return fail("mod_drop: target level %d not in [1,%d]", L_target, in->L);
+    if (c->scheme != B200HE_CKKS) return fail("mod_drop: CKKS only (BFV mod-switch rescales: use rescale_to_next)");
+    CK(cudaSetDevice(c->device));
+    OutBuf ob(out, in);
+    TRY(ob.shape(in->count, in->size, L_target, in->ntt, in->scale));
+    TRY(copy_limbs(c, in->d, in->ct_words(), ob.ptr(), (size_t)in->size * L_target * c->N, nullptr, in->count, in->size, in->L, L_target));
+    ob.commit();
+    return 0;
+}
+
+extern "C" int b200he_gather(b200he_ctx *c, const b200he_batch *in, const uint32_t *idx, uint64_t n, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("gather: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("gather: batch belongs to another context");
+    if (!idx && n > in->count) return fail("gather: n exceeds count");
+    CK(cudaSetDevice(c->device));
+    DevIdx di(c);
+    TRY(di.set(idx, n, in->count, "gather"));
+    OutBuf ob(out, in);
+    TRY(ob.shape(n, in->size, in->L, in->ntt, in->scale));
+    TRY(copy_limbs(c, in->d, in->ct_words(), ob.ptr(), in->ct_words(), di.d, n, in->size, in->L, in->L));
+    ob.commit();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ key switching (K6)
+// out[b] = (add0[b], add1[b]) + KeySwitch(target[b])  for b < B, at level L.
+//   target: [L][N] per ciphertext (stride t_stride), NTT form (CKKS) or coefficient form (BFV)
+//   add0/add1: per-ciphertext addends (stride add_stride) or nullptr (zero)
+//   out: [2][L][N] per ciphertext (stride out_stride); out may alias add0/add1 element-for-element
+static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t t_stride, const u64 *key, const u64 *add0, const u64 *add1,
+                      size_t add_stride, u64 *out, size_t out_stride)
+{
+    const size_t N = c->N, K = c->K;
+    const bool ckks = c->scheme == B200HE_CKKS;
+    // scratch per ciphertext: tcoef [L][N] (CKKS), acc [2][L+1][N], rp [2][N]
+    const size_t w_t = ckks ? (size_t)L * N : 0, w_acc = 2 * (size_t)(L + 1) * N, w_rp = 2 * N;
+    const size_t per_ct = (w_t + w_acc + w_rp) * 8;
+    size_t chunk = c->workspace / per_ct;
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    u64 *ws = (u64 *)c->pool.get(chunk * per_ct);
+    if (!ws) return fail("key_switch: out of device memory for %zu bytes of workspace", chunk * per_ct);
+    u64 *tcoef = ws, *acc = ws + chunk * w_t, *rp = acc + chunk * w_acc;
+    int rc = 0;
+    for (size_t b0 = 0; b0 < B && !rc; b0 += chunk) {
+        const size_t nb = (B - b0 < chunk) ? B - b0 : chunk;
+        const u64 *tg = target + b0 * t_stride;
+        KsInnerArgs A{};
+        if (ckks) {
+            rc = ntt_inv(c, tg, tcoef, nb * L, t_stride, (size_t)L * N, L, 0, INV_PLAIN);
+            if (rc) break;
+            A.tcoef = tcoef; A.tcoef_stride = (size_t)L * N; A.target = tg; A.target_stride = t_stride;
+        } else {
+            A.tcoef = tg; A.tcoef_stride = t_stride; A.target = nullptr; A.target_stride = 0;
+        }
+        A.key = key; A.acc = acc; A.L = L; A.K = (int)K;
+        NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_KS_INNER, k_ks_inner<LG>, (unsigned)((nb * (L + 1)) << c->c), NttCfg<LG>::THREADS,
+                               NttCfg<LG>::SMEM_BYTES, c->T, A, c->c));
+        if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: k_ks_inner launch failed"); break; }
+        // rounded special-prime limb in coefficient form
+        rc = ntt_inv(c, acc + (size_t)L * N, rp, nb * 2, (size_t)(L + 1) * N, N, 1, (int)K - 1, INV_ADDHALF);
+        if (rc) break;
+        ModDownArgs D{};
+        D.rp = rp; D.base = acc; D.base_ct_stride = w_acc; D.base_poly_stride = (size_t)(L + 1) * N;
+        D.addend[0] = add0 ? add0 + b0 * add_stride : nullptr;
+        D.addend[1] = add1 ? add1 + b0 * add_stride : nullptr;
+        D.add_ct_stride = add_stride;
+        D.out = out + b0 * out_stride; D.out_ct_stride = out_stride; D.out_poly_stride = (size_t)L * N;
+        D.P = 2; D.nJ = L; D.x = (int)K - 1;
+        if (ckks) {
+            NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown<LG>, (unsigned)((nb * 2 * L) << c->c), NttCfg<LG>::THREADS,
+                                   NttCfg<LG>::SMEM_BYTES, c->T, D, c->c));
+        } else {
+            // BFV: accumulators back to coefficient form (in place, unsplit per-limb strides), then elementwise mod-down
+            rc = ntt_inv(c, acc, acc, nb * 2 * L, (size_t)(L + 1) * N, (size_t)(L + 1) * N, L, 0, INV_PLAIN);
+            if (rc) break;
+            LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown_coeff, blocks_for(nb * 2 * L * N / 2), 256, 0, c->T, D, nb);
+        }
+        if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: mod-down launch failed"); break; }
+    }
+    c->pool.put(ws);
+    return rc;
+}
+
+extern "C" int b200he_relinearize(b200he_ctx *c, const b200he_batch *in, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("relinearize: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("relinearize: batch belongs to another context");
+    CK(cudaSetDevice(c->device));
+    if (in->size == 2) {   // SEAL: nothing to do (R/src/engine/seal_context.cpp:390)
+        if (out == in) return 0;
+        TRY(batch_shape(out, in->count, 2, in->L, in->ntt, in->scale));
+        return copy_limbs(c, in->d, in->ct_words(), out->d, in->ct_words(), nullptr, in->count, 2, in->L, in->L);
+    }
+    if (in->size != 3) return fail("relinearize: ciphertext size must be 2 or 3");
+    if (!c->relin) return fail("relinearize: no relinearization key uploaded");
+    if ((c->scheme == B200HE_CKKS) != (in->ntt != 0)) return fail("relinearize: wrong NTT form for scheme");
+    OutBuf ob(out, in);
+    TRY(ob.shape(in->count, 2, in->L, in->ntt, in->scale));
+    const size_t LN = (size_t)in->L * c->N;
+    TRY(key_switch(c, in->L, in->count, in->d + 2 * LN, 3 * LN, c->relin, in->d, in->d + LN, 3 * LN, ob.ptr(), 2 * LN));
+    ob.commit();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ Galois (K8)
+extern "C" int b200he_apply_galois(b200he_ctx *c, const b200he_batch *in, uint32_t elt, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("apply_galois: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("apply_galois: batch belongs to another context");
+    if (in->size != 2) return fail("apply_galois: ciphertext size must be 2");
+    if (!(elt & 1) || elt >= 2 * c->N) return fail("apply_galois: invalid Galois element %u", elt);
+    auto kit = c->gal.find(elt);
+    if (kit == c->gal.end()) return fail("apply_galois: no Galois key for element %u", elt);
+    const bool ckks = c->scheme == B200HE_CKKS;
+    if (ckks != (in->ntt != 0)) return fail("apply_galois: wrong NTT form for scheme");
+    CK(cudaSetDevice(c->device));
+    OutBuf ob(out, in);
+    TRY(ob.shape(in->count, 2, in->L, in->ntt, in->scale));
+    const size_t B = in->count, LN = (size_t)in->L * c->N;
+    if (!B) { ob.commit(); return 0; }
+    u64 *g1 = (u64 *)c->pool.get(B * LN * 8);
+    if (!g1) return fail("apply_galois: out of device memory");
+    GaloisArgs G{};
+    G.src = in->d; G.dst0 = ob.ptr(); G.dst1 = g1; G.src_stride = 2 * LN; G.dst_stride = 2 * LN;
+    G.elt = elt; G.L = in->L; G.logn = c->logn; G.B = B;
+    int rc = 0;
+    if (ckks) {
+        rc = galois_table(c, elt, &G.table);
+        if (!rc) LAUNCH(c, B200HE_KERN_GALOIS, k_galois_ntt, blocks_for(B * 2 * LN), 256, 0, c->T, G);
+    } else
+        LAUNCH(c, B200HE_KERN_GALOIS, k_galois_coeff, blocks_for(B * 2 * LN), 256, 0, c->T, G);
+    if (!rc && cudaGetLastError() != cudaSuccess) rc = fail("apply_galois: launch failed");
+    if (!rc) rc = key_switch(c, in->L, B, g1, LN, kit->second, ob.ptr(), nullptr, 2 * LN, ob.ptr(), 2 * LN);
+    c->pool.put(g1);
+    if (rc) return rc;
+    ob.commit();
+    return 0;
+}
+
+// SEAL GaloisTool::get_elt_from_step
+static u32 elt_from_step(const b200he_ctx *c, int step)
+{
+    const u32 m = 2 * c->N, half = c->N / 2;
+    if (step == 0) return m - 1;
+    const u32 pos = (u32)(step < 0 ? -step : step);
+    if (pos >= half) return 0;
+    const u32 e = step < 0 ? half - pos : pos;
+    u64 g = 1;
+    for (u32 i = 0; i < e; i++) g = (g * 3) & (m - 1);
+    return (u32)g;
+}
+
+static int rotate_rec(b200he_ctx *c, const b200he_batch *in, int step, b200he_batch *out)
+{
+    const u32 elt = elt_from_step(c, step);
+    if (!elt) return fail("rotate: step %d out of range", step);
+    if (c->gal.count(elt)) return b200he_apply_galois(c, in, elt, out);
+    // SEAL Evaluator::rotate_internal: non-adjacent form of the step, least significant term first
+    std::vector<int> terms;
+    {
+        int v = step < 0 ? -step : step;
+        for (int i = 0; v; i++) {
+            const int z = (v & 1) ? 2 - (v & 3) : 0;
+            v = (v - z) >> 1;
+            if (z) terms.push_back((step < 0 ? -z : z) * (1 << i));
+        }
+    }
+    if (terms.size() == 1) return fail("rotate: Galois key for step %d missing", step);
+    const b200he_batch *cur = in;
+    for (int term : terms) {
+        if ((u32)(term < 0 ? -term : term) == c->N / 2) continue;
+        TRY(rotate_rec(c, cur, term, out));
+        cur = out;
+    }
+    if (cur == in && out != in) return b200he_gather(c, in, nullptr, in->count, out);
+    return 0;
+}
+
+extern "C" int b200he_rotate(b200he_ctx *c, const b200he_batch *in, int step, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("rotate: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("rotate: batch belongs to another context");
+    if (in->size != 2) return fail("rotate: ciphertext size must be 2");
+    if (step == 0) return out == in ? 0 : b200he_gather(c, in, nullptr, in->count, out);
+    return rotate_rec(c, in, step, out);
+}
+extern "C" int b200he_rotate_columns(b200he_ctx *c, const b200he_batch *in, b200he_batch *out)
+{
+    if (!c) return fail("rotate_columns: NULL argument");
+    return b200he_apply_galois(c, in, 2 * c->N - 1, out);
+}
+
+// SEALContextWrapper::accumulateCKKS / accumulateBFV (R/src/engine/seal_context.cpp:289-347)
+extern "C" int b200he_accumulate(b200he_ctx *c, b200he_batch *io, uint64_t count)
+{
+    if (!c || !io) return fail("accumulate: NULL argument");
+    if (io->ctx != c) return fail("accumulate: batch belongs to another context");
+    const bool ckks = c->scheme == B200HE_CKKS;
+    const uint64_t slots = c->N / 2;
+    if (count == 0) return fail("accumulate: count == 0 (the reference substitutes a fresh encryption of zero; do that on the host)");
+    uint64_t rows = count > slots ? slots : count;
+    int rot = 0;
+    while ((uint64_t(1) << rot) < rows) rot++;
+    b200he_batch *tmp = nullptr;
+    TRY(b200he_batch_create(c, &tmp));
+    int rc = 0;
+    for (int k = 0; k < rot && !rc; k++) {
+        rc = b200he_rotate(c, io, 1 << k, tmp);
+        if (!rc) rc = b200he_add(c, io, nullptr, tmp, nullptr, io->count, io);
+    }
+    if (!rc && !ckks && count > slots) {
+        rc = b200he_rotate_columns(c, io, tmp);
+        if (!rc) rc = b200he_add(c, io, nullptr, tmp, nullptr, io->count, io);
+    }
+    b200he_batch_destroy(tmp);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------ rescale (K9)
+extern "C" int b200he_rescale_to_next(b200he_ctx *c, const b200he_batch *in, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("rescale: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("rescale: batch belongs to another context");
+    if (in->L < 2) return fail("rescale: already at the last level");
+    const bool ckks = c->scheme == B200HE_CKKS;
+    if (ckks != (in->ntt != 0)) return fail("rescale: wrong NTT form for scheme");
+    CK(cudaSetDevice(c->device));
+    const int L = in->L, P = in->size;
+    const size_t N = c->N, B = in->count;
+    OutBuf ob(out, in);
+    TRY(ob.shape(B, P, L - 1, in->ntt, ckks ? in->scale / (double)c->mods[L - 1].q : in->scale));
+    if (!B) { ob.commit(); return 0; }
+    size_t chunk = c->workspace / (P * N * 8);
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    u64 *rp = (u64 *)c->pool.get(chunk * P * N * 8);
+    if (!rp) return fail("rescale: out of device memory");
+    int rc = 0;
+    for (size_t b0 = 0; b0 < B && !rc; b0 += chunk) {
+        const size_t nb = B - b0 < chunk ? B - b0 : chunk;
+        const u64 *src = in->d + b0 * in->ct_words();
+        ModDownArgs D{};
+        D.base = src; D.base_ct_stride = in->ct_words(); D.base_poly_stride = (size_t)L * N;
+        D.addend[0] = D.addend[1] = nullptr; D.add_ct_stride = 0;
+        D.out = ob.ptr() + b0 * (size_t)P * (L - 1) * N; D.out_ct_stride = (size_t)P * (L - 1) * N; D.out_poly_stride = (size_t)(L - 1) * N;
+        D.P = P; D.nJ = L - 1; D.x = L - 1;
+        if (ckks) {
+            rc = ntt_inv(c, src + (size_t)(L - 1) * N, rp, nb * P, (size_t)L * N, N, 1, L - 1, INV_ADDHALF);
+            if (rc) break;
+            D.rp = rp;
+            NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown<LG>, (unsigned)((nb * P * (L - 1)) << c->c), NttCfg<LG>::THREADS,
+                                   NttCfg<LG>::SMEM_BYTES, c->T, D, c->c));
+        } else {
+            // coefficient form: rp = last + q_last/2 mod q_last, elementwise
+            D.rp = nullptr; D.rp_raw = src + (size_t)(L - 1) * N; D.rp_raw_stride = (size_t)L * N;
+            LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown_coeff, blocks_for(nb * P * (L - 1) * N / 2), 256, 0, c->T, D, nb);
+        }
+        if (cudaGetLastError() != cudaSuccess) rc = fail("rescale: launch failed");
+    }
+    c->pool.put(rp);
+    if (rc) return rc;
+    ob.commit();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ BFV multiply (K5)
+#include "behz_host.inl"
+
+// ------------------------------------------------------------------------------------ measurement hooks
+extern "C" uint64_t b200he_launch_count(const b200he_ctx *c) { return c ? c->launches : 0; }
+extern "C" int b200he_profile_begin(b200he_ctx *c)
+{
+    if (!c) return fail("profile_begin: ctx NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    c->recs.clear();
+    c->prof = true;
+    return 0;
+}
+extern "C" int b200he_profile_end(b200he_ctx *c, double *ms, uint64_t *launches)
+{
+    if (!c || !ms || !launches) return fail("profile_end: NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->prof = false;
+    for (int i = 0; i < B200HE_KERN_COUNT; i++) { ms[i] = 0; launches[i] = 0; }
+    for (auto &r : c->recs) {
+        float t = 0;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.cls] += t;
+        launches[r.cls]++;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    c->recs.clear();
+    return 0;
+}
+extern "C" const char *b200he_kernel_name(int k)
+{
+    static const char *names[B200HE_KERN_COUNT] = { "k_ntt_fwd", "k_ntt_inv", "k_ntt_inv_tail", "k_ks_inner", "k_moddown",
+                                                    "k_ew", "k_tensor", "k_galois", "k_copy_limbs", "k_behz" };
+    return (k >= 0 && k < B200HE_KERN_COUNT) ? names[k] : "?";
+}

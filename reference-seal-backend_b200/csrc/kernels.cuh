@@ -1,0 +1,463 @@
+// kernels.cuh -- sm_100a kernels of the ciphertext-evaluation hot path.
+//
+// Kernel <-> SEAL routine map:
+//   k_ntt_fwd            K1  ntt_negacyclic_harvey
+//   k_ntt_inv (+tail)    K2  inverse_ntt_negacyclic_harvey (+ "+q/2" of mod-down/rescale fused)
+//   k_ew / k_tensor      K3/K4/K11  add/sub/dyadic product, ckks_multiply, multiply_plain, add_plain
+//   k_ks_inner           K6 step 2: lift digit, NTT, inner product with the key (digits never leave the SM)
+//   k_moddown            K6 step 3 and K9: NTT of the rounded last limb fused with subtract, *q_last^{-1}, add
+//   k_galois_*           K8 apply_galois_ntt / apply_galois
+//
+// CTA shape.  Every NTT-bearing kernel runs 512-thread CTAs (N <= 8192: N/16 threads) that
+// own a local transform of n_loc = min(N, 8192) coefficients: 64 KiB of shared memory, 16
+// coefficients per thread in registers.  For N = 16384 / 32768 a limb is split over 2 / 4
+// independent CTAs: after the first c = log2(N/n_loc) Cooley-Tukey stages the transform
+// decomposes into 2^c independent sub-transforms on contiguous output ranges, so CTA r
+// recomputes those c stages for its own range straight from global memory (c+1... inputs per
+// output, second reader hits L2) and never talks to its siblings.  The inverse direction
+// runs the local stages per 8192-chunk and finishes the last c stages in an elementwise
+// tail kernel.
+#pragma once
+#include "ntt_core.cuh"
+
+namespace b200he {
+
+struct Tables {
+    const Mod *mods;          // [M]
+    const ulonglong2 *tw;     // [M][N]  forward twiddles (w, shoup)
+    const ulonglong2 *itw;    // [M][N]  inverse twiddles; itw[0] = (w1^{-1} N^{-1}, shoup)
+    const ulonglong2 *qinv;   // [M][M]  qinv[x*M + j] = (q_x^{-1} mod q_j, shoup)
+    const u64 *halfmod;       // [M][M]  halfmod[x*M + j] = (q_x >> 1) mod q_j
+    int N, M;
+};
+
+__device__ __forceinline__ u64 *dyn_smem()
+{
+#ifdef B200HE_EMU
+    return reinterpret_cast<u64 *>(emu::block_smem());
+#else
+    extern __shared__ __align__(16) unsigned char b200he_smem[];
+    return reinterpret_cast<u64 *>(b200he_smem);
+#endif
+}
+
+// Input transforms fused into the first-pass load.
+struct PreNone { __device__ __forceinline__ u64 operator()(u64 v) const { return v; } };
+struct PreReduce {   // v mod q (lift of a digit into another modulus, SEAL modulo_poly_coeffs)
+    Mod m;
+    __device__ __forceinline__ u64 operator()(u64 v) const { return reduce64(v, m); }
+};
+struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_last/2 mod q))
+    Mod m;
+    u64 fix;
+    __device__ __forceinline__ u64 operator()(u64 v) const { return reduce64(v, m) + fix; }
+};
+
+// Load the pass-0 register layout of local chunk r of a limb split 2^c ways, computing the
+// first c global stages on the fly.  src points at the limb (N_glob coefficients).
+template <int LOGN, class Pre>
+__device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restrict__ src, int c, int r, int tid,
+                                               const ulonglong2 *__restrict__ tw, u64 q, u64 two_q, Pre pre)
+{
+    constexpr int NL = 1 << LOGN;
+    if (c == 0) {
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            ulonglong2 v = ldg2(src + e);
+            x[reg] = pre(v.x);
+            x[reg + 1] = pre(v.y);
+        });
+    } else if (c == 1) {
+        const ulonglong2 w = ld_tw(tw + 1);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            ulonglong2 a = ldg2(src + e), b = ldg2(src + e + NL);
+            u64 a0 = pre(a.x), a1 = pre(a.y), b0 = pre(b.x), b1 = pre(b.y);
+            ct_bfly(a0, b0, w.x, w.y, q, two_q);
+            ct_bfly(a1, b1, w.x, w.y, q, two_q);
+            x[reg] = r ? b0 : a0;
+            x[reg + 1] = r ? b1 : a1;
+        });
+    } else {
+        const ulonglong2 w1 = ld_tw(tw + 1), w2 = ld_tw(tw + 2 + (r >> 1));
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            ulonglong2 v0 = ldg2(src + e), v1 = ldg2(src + e + NL), v2 = ldg2(src + e + 2 * NL), v3 = ldg2(src + e + 3 * NL);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                u64 a0 = pre(h ? v0.y : v0.x), a1 = pre(h ? v1.y : v1.x), a2 = pre(h ? v2.y : v2.x), a3 = pre(h ? v3.y : v3.x);
+                ct_bfly(a0, a2, w1.x, w1.y, q, two_q);
+                ct_bfly(a1, a3, w1.x, w1.y, q, two_q);
+                u64 u = (r >> 1) ? a2 : a0, v = (r >> 1) ? a3 : a1;
+                ct_bfly(u, v, w2.x, w2.y, q, two_q);
+                x[reg + h] = (r & 1) ? v : u;
+            }
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------ K1
+// dst[w] = NTT(src[w]) for w < nlimbs; modulus id = mod_base + (w % L).  grid = nlimbs << c.
+// Limb w lives at base + (w / L) * outer + (w % L) * N  (outer = L*N for a contiguous batch; a larger
+// outer stride addresses one limb per polynomial, e.g. the special-prime limb of the key-switch accumulator).
+template <int LOGN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
+                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base, int c)
+{
+    constexpr int NL = 1 << LOGN;
+    u64 *sm = dyn_smem();
+    const int tid = threadIdx.x;
+    const int w = blockIdx.x >> c, r = blockIdx.x & ((1 << c) - 1);
+    const int mid = mod_base + (w % L);
+    const Mod m = T.mods[mid];
+    const ulonglong2 *tw = T.tw + (size_t)mid * T.N;
+    u64 x[16];
+    load_fwd_split<LOGN>(x, src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N, c, r, tid, tw, m.q, m.two_q, PreNone());
+    ntt_fwd_regs_split<LOGN>(x, sm, tw, m.q, m.two_q, tid, c, r);
+    u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
+    for_pairs_contig(tid, [&](int reg, int e) {
+        st2(out + e, csub(csub(x[reg], m.two_q), m.q), csub(csub(x[reg + 1], m.two_q), m.q));
+    });
+}
+
+// ------------------------------------------------------------------------------------ K2
+enum { INV_PLAIN = 0, INV_ADDHALF = 1 };
+__device__ __forceinline__ u64 inv_finish(u64 v /* [0,2q) */, const Mod &m, int mode)
+{
+    v = csub(v, m.q);
+    if (mode == INV_ADDHALF) v = csub(v + (m.q >> 1), m.q);
+    return v;
+}
+// c == 0: dst = iNTT(src) (finished).  c > 0: dst = partial (local stages only, values in [0,2q)).
+template <int LOGN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
+                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base, int c, int mode)
+{
+    constexpr int NL = 1 << LOGN;
+    u64 *sm = dyn_smem();
+    const int tid = threadIdx.x;
+    const int w = blockIdx.x >> c, r = blockIdx.x & ((1 << c) - 1);
+    const int mid = mod_base + (w % L);
+    const Mod m = T.mods[mid];
+    const ulonglong2 *itw = T.itw + (size_t)mid * T.N;
+    const u64 *in = src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
+    u64 x[16];
+    for_pairs_contig(tid, [&](int reg, int e) {
+        ulonglong2 v = ldg2(in + e);
+        x[reg] = v.x;
+        x[reg + 1] = v.y;
+    });
+    u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
+    if (c == 0) {
+        ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, mode), inv_finish(x[reg + 1], m, mode)); });
+    } else {
+        ntt_inv_regs_split<LOGN, false>(x, sm, itw, m, tid, c, r);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
+    }
+}
+// Tail of a split inverse: the last c Gentleman-Sande stages across the 2^c chunks, N^{-1}, finish.
+// One thread per coefficient pair of a chunk; in place.  grid covers nlimbs * (N >> c) / 2 threads.
+__global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict__ data, size_t outer, size_t nlimbs, int L, int mod_base, int c, int mode)
+{
+    const size_t chunk = (size_t)T.N >> c, per_limb = chunk / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nlimbs * per_limb) return;
+    const size_t w = gid / per_limb, e = (gid % per_limb) * 2;
+    const int mid = mod_base + (int)(w % L);
+    const Mod m = T.mods[mid];
+    const ulonglong2 *itw = T.itw + (size_t)mid * T.N;
+    u64 *p = data + (w / L) * outer + (w % L) * T.N + e;
+    const ulonglong2 wn = ld_tw(itw);
+    if (c == 1) {
+        ulonglong2 a = ld2(p), b = ld2(p + chunk);
+        u64 s0 = a.x + b.x, d0 = a.x - b.x + m.two_q, s1 = a.y + b.y, d1 = a.y - b.y + m.two_q;
+        st2(p, inv_finish(shoup_lazy(s0, m.ninv, m.ninv_s, m.q), m, mode), inv_finish(shoup_lazy(s1, m.ninv, m.ninv_s, m.q), m, mode));
+        st2(p + chunk, inv_finish(shoup_lazy(d0, wn.x, wn.y, m.q), m, mode), inv_finish(shoup_lazy(d1, wn.x, wn.y, m.q), m, mode));
+    } else {
+        ulonglong2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = ld2(p + k * chunk);
+        const ulonglong2 w2 = ld_tw(itw + 2), w3 = ld_tw(itw + 3);
+        u64 o[4][2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            u64 a0 = h ? v[0].y : v[0].x, a1 = h ? v[1].y : v[1].x, a2 = h ? v[2].y : v[2].x, a3 = h ? v[3].y : v[3].x;
+            gs_bfly(a0, a1, w2.x, w2.y, m.q, m.two_q);
+            gs_bfly(a2, a3, w3.x, w3.y, m.q, m.two_q);
+            o[0][h] = shoup_lazy(a0 + a2, m.ninv, m.ninv_s, m.q);
+            o[2][h] = shoup_lazy(a0 - a2 + m.two_q, wn.x, wn.y, m.q);
+            o[1][h] = shoup_lazy(a1 + a3, m.ninv, m.ninv_s, m.q);
+            o[3][h] = shoup_lazy(a1 - a3 + m.two_q, wn.x, wn.y, m.q);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) st2(p + k * chunk, inv_finish(o[k][0], m, mode), inv_finish(o[k][1], m, mode));
+    }
+}
+
+// ------------------------------------------------------------------------------------ K6 step 2
+// acc[b][k][I] = sum_J NTT_{q_I}(t[b][J] mod q_I) (.) key[J][k][I]      (I == L  <->  special prime)
+// CKKS: the I == J term reuses the NTT-form target.  grid = B * (L+1) << c.
+struct KsInnerArgs {
+    const u64 *tcoef;      // target in coefficient form: tcoef + b*tcoef_stride + J*N
+    size_t tcoef_stride;
+    const u64 *target;     // NTT-form target (CKKS) or nullptr (BFV): target + b*target_stride + J*N
+    size_t target_stride;
+    const u64 *key;        // [Ltop][2][K][N]
+    u64 *acc;              // [B][2][L+1][N]
+    int L, K;
+};
+template <int LOGN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T, KsInnerArgs A, int c)
+{
+    constexpr int NL = 1 << LOGN;
+    u64 *sm = dyn_smem();
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x & ((1 << c) - 1);
+    const int unit = blockIdx.x >> c;
+    const int L = A.L, b = unit / (L + 1), I = unit % (L + 1);
+    const int ki = (I == L) ? A.K - 1 : I;
+    const Mod m = T.mods[ki];
+    const ulonglong2 *tw = T.tw + (size_t)ki * T.N;
+    const size_t N = T.N, off = (size_t)r * NL;
+    u64 a0[16], a1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a0[i] = a1[i] = 0;
+    for (int J = 0; J < L; J++) {
+        u64 x[16];
+        if (A.target && I == J) {
+            const u64 *tp = A.target + (size_t)b * A.target_stride + (size_t)J * N + off;
+            for_pairs_contig(tid, [&](int reg, int e) {
+                ulonglong2 v = ldg2(tp + e);
+                x[reg] = v.x;
+                x[reg + 1] = v.y;
+            });
+        } else {
+            const u64 *tp = A.tcoef + (size_t)b * A.tcoef_stride + (size_t)J * N;
+            if (T.mods[J].q > m.q)
+                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m.q, m.two_q, PreReduce{ m });
+            else
+                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m.q, m.two_q, PreNone());
+            ntt_fwd_regs_split<LOGN>(x, sm, tw, m.q, m.two_q, tid, c, r);
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = csub(csub(x[i], m.two_q), m.q);
+            __syncthreads();   // shared buffer is reused by the next digit
+        }
+        const u64 *k0 = A.key + (((size_t)J * 2 + 0) * A.K + ki) * N + off;
+        const u64 *k1 = A.key + (((size_t)J * 2 + 1) * A.K + ki) * N + off;
+        for_pairs_contig(tid, [&](int reg, int e) {
+            ulonglong2 v0 = ldg2(k0 + e), v1 = ldg2(k1 + e);
+            a0[reg] = mad_mod(x[reg], v0.x, a0[reg], m);
+            a0[reg + 1] = mad_mod(x[reg + 1], v0.y, a0[reg + 1], m);
+            a1[reg] = mad_mod(x[reg], v1.x, a1[reg], m);
+            a1[reg + 1] = mad_mod(x[reg + 1], v1.y, a1[reg + 1], m);
+        });
+    }
+    u64 *o0 = A.acc + (((size_t)b * 2 + 0) * (L + 1) + I) * N + off;
+    u64 *o1 = A.acc + (((size_t)b * 2 + 1) * (L + 1) + I) * N + off;
+    for_pairs_contig(tid, [&](int reg, int e) {
+        st2(o0 + e, a0[reg], a0[reg + 1]);
+        st2(o1 + e, a1[reg], a1[reg + 1]);
+    });
+}
+
+// ------------------------------------------------------------------------------------ K6 step 3 / K9
+// out[b][p][j] = (addend[b][p][j] +) (base[b][p][j] - NTT_{q_j}(rp[b][p] mod q_j + fix)) * q_x^{-1} mod q_j
+// rp = rounded last limb in coefficient form ((iNTT(last) + q_x/2) mod q_x), x = modulus id of the dropped prime.
+// Key switch:  base = acc (stride over L+1 limbs), addend = input ct component (or none), x = K-1.
+// Rescale:     base = input ct, addend = none, x = L-1.       grid = B * P * nJ << c.
+struct ModDownArgs {
+    const u64 *rp;         // [B][P][N]  (k_moddown_coeff: may be nullptr, then rp_raw is used)
+    const u64 *rp_raw;     // un-rounded last limb, coefficient form: rp_raw + (b*P + p)*rp_raw_stride
+    size_t rp_raw_stride;
+    const u64 *base;       // base + b*base_ct_stride + p*base_poly_stride + j*N
+    size_t base_ct_stride, base_poly_stride;
+    const u64 *addend[2];  // per poly (P <= 2 when addend used) or nullptr; addend[p] + b*add_ct_stride + j*N
+    size_t add_ct_stride;
+    u64 *out;              // out + b*out_ct_stride + p*out_poly_stride + j*N
+    size_t out_ct_stride, out_poly_stride;
+    int P, nJ, x;          // x = modulus id of the dropped prime
+};
+template <int LOGN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, ModDownArgs A, int c)
+{
+    constexpr int NL = 1 << LOGN;
+    u64 *sm = dyn_smem();
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x & ((1 << c) - 1);
+    int unit = blockIdx.x >> c;
+    const int j = unit % A.nJ;
+    unit /= A.nJ;
+    const int p = unit % A.P, b = unit / A.P;
+    const Mod m = T.mods[j];
+    const ulonglong2 *tw = T.tw + (size_t)j * T.N;
+    const size_t N = T.N, off = (size_t)r * NL;
+    const u64 fix = m.q - T.halfmod[(size_t)A.x * T.M + j];
+    const ulonglong2 qi = T.qinv[(size_t)A.x * T.M + j];
+    u64 x[16];
+    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m.q, m.two_q, PreReduceFix{ m, fix });
+    ntt_fwd_regs_split<LOGN>(x, sm, tw, m.q, m.two_q, tid, c, r);
+    const u64 *bp = A.base + (size_t)b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + off;
+    const u64 *ap = A.addend[p] ? A.addend[p] + (size_t)b * A.add_ct_stride + (size_t)j * N + off : nullptr;
+    u64 *op = A.out + (size_t)b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + off;
+    for_pairs_contig(tid, [&](int reg, int e) {
+        ulonglong2 bv = ldg2(bp + e);
+        u64 u0 = csub(csub(x[reg], m.two_q), m.q), u1 = csub(csub(x[reg + 1], m.two_q), m.q);
+        u64 v0 = shoup(sub_mod(bv.x, u0, m.q), qi.x, qi.y, m.q);
+        u64 v1 = shoup(sub_mod(bv.y, u1, m.q), qi.x, qi.y, m.q);
+        if (ap) {
+            ulonglong2 av = ldg2(ap + e);
+            v0 = add_mod(v0, av.x, m.q);
+            v1 = add_mod(v1, av.y, m.q);
+        }
+        st2(op + e, v0, v1);
+    });
+}
+
+// Coefficient-form variant (BFV key switch / BFV mod-switch): no transform, one thread per coefficient pair.
+// base must already be in coefficient form.  grid covers B * P * nJ * N / 2 threads.
+__global__ void __launch_bounds__(256) k_moddown_coeff(Tables T, ModDownArgs A, size_t B)
+{
+    const size_t N = T.N, per_ct = (size_t)A.P * A.nJ * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * per_ct) return;
+    const size_t b = gid / per_ct, rem = (gid % per_ct) * 2;
+    const size_t limb = rem / N, e = rem % N;
+    const int p = (int)(limb / A.nJ), j = (int)(limb % A.nJ);
+    const Mod m = T.mods[j];
+    const u64 fix = m.q - T.halfmod[(size_t)A.x * T.M + j];
+    const ulonglong2 qi = T.qinv[(size_t)A.x * T.M + j];
+    ulonglong2 r;
+    if (A.rp) r = ld2(A.rp + (b * A.P + p) * N + e);
+    else {
+        const Mod mx = T.mods[A.x];
+        r = ld2(A.rp_raw + (b * A.P + p) * A.rp_raw_stride + e);
+        r.x = csub(r.x + (mx.q >> 1), mx.q);
+        r.y = csub(r.y + (mx.q >> 1), mx.q);
+    }
+    const u64 u0 = csub(reduce64(r.x, m) + fix, m.q), u1 = csub(reduce64(r.y, m) + fix, m.q);
+    const ulonglong2 bv = ld2(A.base + b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + e);
+    u64 v0 = shoup(sub_mod(bv.x, u0, m.q), qi.x, qi.y, m.q);
+    u64 v1 = shoup(sub_mod(bv.y, u1, m.q), qi.x, qi.y, m.q);
+    if (A.addend[p]) {
+        const ulonglong2 av = ld2(A.addend[p] + b * A.add_ct_stride + (size_t)j * N + e);
+        v0 = add_mod(v0, av.x, m.q);
+        v1 = add_mod(v1, av.y, m.q);
+    }
+    st2(A.out + b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + e, v0, v1);
+}
+
+// ------------------------------------------------------------------------------------ K3 / K4 / K11
+// Elementwise kernels: one thread per coefficient pair; ciphertext i of the output pairs
+// a[ai[i]] with b[bi[i]] (index maps express the reference's b0 x b1 result grid without copies).
+enum { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2 };
+struct EwArgs {
+    const u64 *a, *b;
+    u64 *out;
+    const u32 *ai, *bi;         // nullable
+    size_t a_stride, b_stride, out_stride;   // words per ciphertext
+    int polys, b_polys;         // polys in out/a; polys in b (1 = plaintext broadcast over polys / only c0 for add)
+    int L, mod_base;
+    size_t n;                   // ciphertexts
+};
+template <int OP> __global__ void __launch_bounds__(256) k_ew(Tables T, EwArgs A)
+{
+    const size_t N = T.N, per_ct = (size_t)A.polys * A.L * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n * per_ct) return;
+    const size_t i = gid / per_ct, rem = (gid % per_ct) * 2;
+    const size_t limb_idx = rem / N, e = rem % N;
+    const int p = (int)(limb_idx / A.L), l = (int)(limb_idx % A.L);
+    const Mod m = T.mods[A.mod_base + l];
+    const size_t ia = A.ai ? A.ai[i] : i, ib = A.bi ? A.bi[i] : i;
+    ulonglong2 va = ld2(A.a + ia * A.a_stride + rem);
+    u64 *o = A.out + i * A.out_stride + rem;
+    if (A.b_polys == 1 && p > 0 && OP != EW_MUL) {   // add_plain / sub_plain touch c0 only
+        st2(o, va.x, va.y);
+        return;
+    }
+    const size_t boff = (A.b_polys == 1 ? 0 : (size_t)p * A.L * N) + (size_t)l * N + e;
+    ulonglong2 vb = ld2(A.b + ib * A.b_stride + boff);
+    if (OP == EW_ADD) st2(o, add_mod(va.x, vb.x, m.q), add_mod(va.y, vb.y, m.q));
+    else if (OP == EW_SUB) st2(o, sub_mod(va.x, vb.x, m.q), sub_mod(va.y, vb.y, m.q));
+    else st2(o, mul_mod(va.x, vb.x, m), mul_mod(va.y, vb.y, m));
+}
+
+// CKKS / NTT-domain tensor product (2 x 2 -> 3): reads 4 polys, writes 3, one pass.
+__global__ void __launch_bounds__(256) k_tensor(Tables T, EwArgs A)
+{
+    const size_t N = T.N, LN = (size_t)A.L * N, per_ct = LN / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n * per_ct) return;
+    const size_t i = gid / per_ct, rem = (gid % per_ct) * 2;
+    const int l = (int)(rem / N);
+    const Mod m = T.mods[A.mod_base + l];
+    const size_t ia = A.ai ? A.ai[i] : i, ib = A.bi ? A.bi[i] : i;
+    const u64 *pa = A.a + ia * A.a_stride + rem, *pb = A.b + ib * A.b_stride + rem;
+    ulonglong2 a0 = ld2(pa), a1 = ld2(pa + LN), b0 = ld2(pb), b1 = ld2(pb + LN);
+    u64 *o = A.out + i * A.out_stride + rem;
+    st2(o, mul_mod(a0.x, b0.x, m), mul_mod(a0.y, b0.y, m));
+    st2(o + LN, mad_mod(a0.x, b1.x, mul_mod(a1.x, b0.x, m), m), mad_mod(a0.y, b1.y, mul_mod(a1.y, b0.y, m), m));
+    st2(o + 2 * LN, mul_mod(a1.x, b1.x, m), mul_mod(a1.y, b1.y, m));
+}
+
+// ------------------------------------------------------------------------------------ K8
+// NTT-form Galois automorphism of a size-2 ciphertext batch: out0 = g(c0) -> dst ct poly 0,
+// g(c1) -> target buffer [B][L][N]; dst poly 1 is produced by the key switch that follows.
+struct GaloisArgs {
+    const u64 *src;       // [B][2][L][N]
+    u64 *dst0;            // g(c0): dst0 + b*dst_stride + l*N
+    u64 *dst1;            // g(c1): dst1 + b*L*N + l*N
+    size_t src_stride, dst_stride;
+    const u32 *table;     // [N] NTT-form permutation (CKKS)
+    u32 elt;              // Galois element (BFV coefficient form)
+    int L, logn;
+    size_t B;
+};
+__global__ void __launch_bounds__(256) k_galois_ntt(Tables T, GaloisArgs A)
+{
+    const size_t N = T.N, per_ct = 2 * (size_t)A.L * N;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.B * per_ct) return;
+    const size_t b = gid / per_ct, rem = gid % per_ct;
+    const size_t p = rem / ((size_t)A.L * N), le = rem % ((size_t)A.L * N), l = le / N, e = le % N;
+    const u64 v = A.src[b * A.src_stride + p * A.L * N + l * N + A.table[e]];
+    if (p == 0) A.dst0[b * A.dst_stride + le] = v;
+    else A.dst1[b * A.L * N + le] = v;
+}
+// Coefficient-form automorphism (BFV): coefficient i moves to i*elt mod N, negated when floor(i*elt/N) is odd.
+__global__ void __launch_bounds__(256) k_galois_coeff(Tables T, GaloisArgs A)
+{
+    const size_t N = T.N, per_ct = 2 * (size_t)A.L * N;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.B * per_ct) return;
+    const size_t b = gid / per_ct, rem = gid % per_ct;
+    const size_t p = rem / ((size_t)A.L * N), le = rem % ((size_t)A.L * N), l = le / N, i = le % N;
+    const u64 q = T.mods[l].q;
+    u64 v = A.src[b * A.src_stride + rem];
+    const u64 raw = (u64)i * A.elt;
+    const size_t idx = raw & (N - 1);
+    if ((raw >> A.logn) & 1) v = v ? q - v : 0;
+    if (p == 0) A.dst0[b * A.dst_stride + l * N + idx] = v;
+    else A.dst1[b * A.L * N + l * N + idx] = v;
+}
+
+// strided copy of polys/limbs (mod_switch_drop_to_next, ciphertext gather): out[i][p][l] = in[idx[i]][p][l], l < L_out
+struct CopyArgs {
+    const u64 *src;
+    u64 *dst;
+    const u32 *idx;
+    size_t src_stride, dst_stride;
+    int polys, L_in, L_out;
+    size_t n;
+};
+__global__ void __launch_bounds__(256) k_copy_limbs(Tables T, CopyArgs A)
+{
+    const size_t N = T.N, per_ct = (size_t)A.polys * A.L_out * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n * per_ct) return;
+    const size_t i = gid / per_ct, rem = (gid % per_ct) * 2;
+    const size_t limb_idx = rem / N, e = rem % N, p = limb_idx / A.L_out, l = limb_idx % A.L_out;
+    const size_t is = A.idx ? A.idx[i] : i;
+    ulonglong2 v = ld2(A.src + is * A.src_stride + (p * A.L_in + l) * N + e);
+    st2(A.dst + i * A.dst_stride + rem, v.x, v.y);
+}
+
+}   // namespace b200he
