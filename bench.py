@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- HEBench samples/s of the ciphertext-evaluation hot path on B200.
+
+Workload (BASELINE.json configs[1]): CKKS element-wise multiply + relinearize + rescale,
+N = 8192, coefficient modulus {60,45,60} (3 limbs at key level, 2 data limbs), 1000 ciphertext
+pairs per GPU per step.  One "sample" = one result ciphertext.  Inputs are synthetic: uniform random
+residues (seed 1234), real key-switching keys from the host FHE stand-in.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            the B200 arm
+    python bench.py --impl reference [...]                          the CPU arm (SEAL-restatement oracle)
+
+N > 1: launched by torchrun, one rank per GPU; the batch is sharded (weak scaling: 1000 pairs per GPU),
+no data-path collective; torch.distributed is used for the barrier and the max-over-ranks time only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "reference-seal-backend_b200"))
+
+N_POLY = 8192
+COEFF_BITS = 45
+DEPTH = 2                 # K = 3 primes {60,45,60}
+BATCH = 1000              # ciphertext pairs per GPU per step
+SEED = 1234
+METRIC = "hebench_samples_per_s_ckks_eltwise_mul_relin_rescale_n8192"
+UNIT = "samples/s"
+CONFIG = {
+    "workload": "CKKS eltwise multiply+relinearize+rescale, N=8192, coeff_modulus {60,45,60}, batch 1000 ciphertext pairs per GPU (BASELINE.json configs[1])",
+    "poly_modulus_degree": N_POLY, "coeff_modulus_bits": [60, 45, 60], "batch_per_gpu": BATCH,
+    "parallelism": "batch-sharded, no collective",
+    "l2_policy": "inputs (2 x 262 MB) + intermediates per step exceed the 126 MB L2; no flush needed",
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.stop = gpu, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def synth_inputs(moduli, n, L, N, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, 2, L, N), dtype=np.uint64)
+    for l in range(L):
+        out[:, :, l, :] = rng.integers(0, int(moduli[l]), size=(n, 2, N), dtype=np.uint64)
+    return out
+
+
+# per-launch algorithmic bytes of each kernel class for this workload (DESIGN.md "Kernels"), W = 8 B
+def algorithmic_bytes(cls, B, L, K, N):
+    W = 8
+    return {
+        "k_tensor": (4 + 3) * L * N * W * B,
+        # three k_ntt_inv launches per step: L limbs (target), 2 (special-prime accumulators), 2 (rescale last limb)
+        "k_ntt_inv": 2 * N * W * B * (L + 2 + 2) / 3.0,
+        # reads target coeff + NTT form, writes 2(L+1) accumulator limbs; key read once per launch
+        "k_ks_inner": (2 * L + 2 * (L + 1)) * N * W * B + 2 * L * (L + 1) * N * W,
+        # two launches per step: key-switch mod-down (rp 2, acc 2L, addend 2L, out 2L) and rescale (rp 2, in 2(L-1), out 2(L-1))
+        "k_moddown": ((2 + 6 * L) + (2 + 4 * (L - 1))) * N * W * B / 2.0,
+    }.get(cls)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import pyb200he as hb
+    from pyb200he.hostfhe import CKKS, Host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torchrun, one rank per GPU")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    host = Host(CKKS, N_POLY, DEPTH, COEFF_BITS, COEFF_BITS, seed=SEED)
+    ctx = hb.Context(CKKS, N_POLY, host.moduli, host.psi, 0, device=local)
+    stream = torch.cuda.Stream(device=local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_relin_key(host.relin_key())
+    L, K, N = host.Ltop, host.K, N_POLY
+    scale = host.scale
+
+    # this rank's shard of the global batch (weak scaling: BATCH pairs per GPU), pinned on the host
+    a_np = synth_inputs(host.moduli, BATCH, L, N, SEED + 2 * rank)
+    b_np = synth_inputs(host.moduli, BATCH, L, N, SEED + 2 * rank + 1)
+    words_in, words_out = 2 * L * N, 2 * (L - 1) * N
+    a_pin = torch.from_numpy(a_np.view(np.int64).reshape(-1)).pin_memory()
+    b_pin = torch.from_numpy(b_np.view(np.int64).reshape(-1)).pin_memory()
+    out_pin = torch.empty(BATCH * words_out, dtype=torch.int64).pin_memory()
+    A, B, R = hb.Batch(ctx), hb.Batch(ctx), hb.Batch(ctx)
+    A.resize(BATCH, 2, L, True, scale)
+    B.resize(BATCH, 2, L, True, scale)
+
+    def upload():
+        A.upload_from(a_pin.data_ptr(), 0, BATCH)
+        B.upload_from(b_pin.data_ptr(), 0, BATCH)
+
+    def step():
+        ctx.multiply(A, B, out=R)
+        ctx.relinearize(R, out=R)
+        ctx.rescale_to_next(R, out=R)
+
+    def e2e_step():
+        upload()
+        step()
+        R.download_to(out_pin.data_ptr(), 0, BATCH)   # blocks until the results are on the host
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    upload()
+    ctx.sync()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.sync()
+
+    # ---- device-resident timing: inputs already in HBM, CUDA events on the launching stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = ctx.launch_count()
+    with ClockSampler(local) as clk:
+        ctx.profile_begin()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        prof = ctx.profile_end()
+        barrier()
+    launches = ctx.launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = clk.summary()
+
+    # ---- end to end through the C ABI with host buffers (pinned): H2D + compute + D2H per step
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+
+    # sanity: the timed path produced the bits the step defines (first result vs a fresh single-ciphertext run)
+    chk = ctx.multiply(ctx.batch(a_np[:1], scale=scale), ctx.batch(b_np[:1], scale=scale))
+    ctx.relinearize(chk, out=chk)
+    ctx.rescale_to_next(chk, out=chk)
+    got = out_pin.numpy()[:words_out].view(np.uint64)
+    assert np.array_equal(got, chk.download().reshape(-1)), "timed path result differs from a fresh evaluation"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    samples = BATCH * world * args.steps
+    value = samples / (ms_total / 1e3)
+    peak, peak_src = peaks()
+    # dominant kernel class of the step
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    top_name, (top_ms, top_n) = top
+    alg = algorithmic_bytes(top_name, BATCH, L, K, N)
+    achieved = alg / (top_ms / top_n / 1e3) / 1e9 if alg else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(top_name)
+    ntt_limbs = {"k_ks_inner": 4, "k_moddown": 3, "k_ntt_inv": (L + 4) / 3.0}.get(top_name, 0) * BATCH
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic (uniform random residues, seed 1234; real relinearization key)",
+        "config": CONFIG, "clocks": clocks,
+        "e2e": {"value": samples / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * words_in * 8,
+                "d2h_bytes_per_step": BATCH * words_out * 8, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "avg_launch_ms": top_ms / top_n, "share_of_step": top_ms / (ms_total_local(prof)),
+                     "limb_ntts_per_s": ntt_limbs / (top_ms / top_n / 1e3) if ntt_limbs else None},
+        "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+    }
+    line["cpu_baseline"] = cpu_baseline(budget_s=12.0) if world == 1 else None
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def ms_total_local(prof):
+    return sum(v[0] for v in prof.values())
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def oracle_setup():
+    """the SEAL-restatement oracle (oracle/, test infrastructure) -- used here only as the timed CPU baseline"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    from helpers import CKKS, Oracle
+    from pyb200he.hostfhe import Host
+    host = Host(CKKS, N_POLY, DEPTH, COEFF_BITS, COEFF_BITS, seed=SEED)
+    orc = Oracle(CKKS, N_POLY, host.moduli)
+    return np, host, orc
+
+
+def cpu_sample(np, host, orc, n, threads):
+    a = synth_inputs(host.moduli, n, host.Ltop, N_POLY, SEED).reshape(-1)
+    b = synth_inputs(host.moduli, n, host.Ltop, N_POLY, SEED + 1).reshape(-1)
+    key = host.relin_key()
+    t = time.perf_counter()
+    orc.mul_relin_rescale(host.Ltop, n, a, b, key, threads=threads)
+    return time.perf_counter() - t
+
+
+def cpu_baseline(budget_s=12.0):
+    np, host, orc = oracle_setup()
+    threads = orc.o.orc_max_threads()
+    probe = 4 * threads
+    dt = cpu_sample(np, host, orc, probe, threads)
+    n = int(max(probe, min(BATCH, probe * budget_s / max(dt, 1e-6))))
+    dt = cpu_sample(np, host, orc, n, threads)
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} of the {BATCH} ciphertext pairs of one step, {threads} OpenMP threads over the batch like the reference's operate(); "
+                      "SEAL-restatement oracle (SEAL itself is not buildable offline)"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    np, host, orc = oracle_setup()
+    threads = orc.o.orc_max_threads()
+    probe = 4 * threads
+    dt = cpu_sample(np, host, orc, probe, threads)
+    total_steps = max(args.warmup, 0) + args.steps
+    per_step_budget = min(20.0, 150.0 / max(total_steps, 1))
+    n = int(max(threads, min(BATCH, probe * per_step_budget / max(dt, 1e-6))))
+    for _ in range(args.warmup):
+        cpu_sample(np, host, orc, n, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_sample(np, host, orc, n, threads)
+    value = n * args.steps / t
+    sample = f"{n} of the {BATCH} ciphertext pairs per step, {threads} OpenMP threads (SEAL-restatement oracle; SEAL not buildable offline)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic (uniform random residues, seed 1234)", "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,28 +138,33 @@ __device__ __forceinline__ void bfly_inv(u64 (&x)[16], const ulonglong2 *__restr
     typedef Pass<LOGN, P> G;
     const int hi = G::hi(tid);
     const u64 q = m.q, two_q = m.two_q;
+    constexpr bool FOLD = FINAL && P == 0;   // this pass ends with global stage 0
 #pragma unroll
-    for (int u = G::K - 1; u >= 0; u--) {
+    for (int u = G::K - 1; u >= (FOLD ? 1 : 0); u--) {
         const int half = 1 << (G::K - 1 - u);
 #pragma unroll
         for (int blk = 0; blk < (1 << u); blk++) {
-            const bool last = FINAL && P == 0 && u == 0;
-            const ulonglong2 w = ld_tw(last ? itw : itw + (pre << (G::S + u)) + (hi << u) + blk);
+            const ulonglong2 w = ld_tw(itw + (pre << (G::S + u)) + (hi << u) + blk);
 #pragma unroll
             for (int jj = 0; jj < half; jj++) {
                 const int j0 = blk * 2 * half + jj, j1 = j0 + half;
 #pragma unroll
-                for (int c = 0; c < G::C; c++) {
-                    u64 &a = x[j0 * G::C + c], &b = x[j1 * G::C + c];
-                    if (last) {
-                        u64 s = a + b, d = a - b + two_q;
-                        a = shoup_lazy(s, m.ninv, m.ninv_s, q);
-                        b = shoup_lazy(d, w.x, w.y, q);
-                    } else
-                        gs_bfly(a, b, w.x, w.y, q, two_q);
-                }
+                for (int c = 0; c < G::C; c++) gs_bfly(x[j0 * G::C + c], x[j1 * G::C + c], w.x, w.y, q, two_q);
             }
         }
+    }
+    if constexpr (FOLD) {
+        const ulonglong2 w = ld_tw(itw);
+        constexpr int half = 1 << (G::K - 1);
+#pragma unroll
+        for (int jj = 0; jj < half; jj++)
+#pragma unroll
+            for (int c = 0; c < G::C; c++) {
+                u64 &a = x[jj * G::C + c], &b = x[(jj + half) * G::C + c];
+                const u64 s = a + b, d = a - b + two_q;
+                a = shoup_lazy(s, m.ninv, m.ninv_s, q);
+                b = shoup_lazy(d, w.x, w.y, q);
+            }
     }
 }
 

@@ -269,3 +269,28 @@ def case_errors(env):
     e = env.ctx.batch(np.zeros(0, dtype=np.uint64), L=L)
     assert env.ctx.add(e, e).count == 0
     assert env.ctx.relinearize(env.ctx.batch(np.zeros(0, dtype=np.uint64), size=3, L=L)).count == 0
+
+
+def case_decrypt_level(lib, N, n=100):
+    """value-level check with real keys (host FHE stand-in): the dot-product pipeline decrypts to the
+    cleartext dot product, and multiply+relinearize+rescale to the slot-wise product"""
+    from helpers import Host
+    h = Host(CKKS, N, 2, 45, 45)
+    ctx = hb.Context(CKKS, N, h.moduli, h.psi, 0, lib=lib)
+    ctx.set_relin_key(h.relin_key())
+    for e in h.galois_elts():
+        ctx.set_galois_key(e, h.galois_key(e))
+    rng = np.random.default_rng(7)
+    u, v = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    A = ctx.batch(h.enc_vec(u), scale=h.scale)
+    B = ctx.batch(h.enc_vec(v), scale=h.scale)
+    r = ctx.multiply(A, B)
+    ctx.relinearize(r, out=r)
+    s = ctx.rescale_to_next(r)
+    dec = h.dec_vec(s.download()[0].reshape(-1), 2, 1, scale=s.scale)
+    assert np.max(np.abs(dec[:n] - u * v)) < 1e-4
+    ctx.accumulate(r, n)
+    dec = h.dec_vec(r.download()[0].reshape(-1), 2, 2, scale=r.scale)
+    want = float(np.dot(u, v))
+    assert abs(dec[0] - want) < 1e-4 * max(1.0, abs(want)), (dec[0], want)
+    ctx.close()

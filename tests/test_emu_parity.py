@@ -100,3 +100,7 @@ def test_split_limb(emu_lib):
         parity.case_relinearize(env, n=1)
         parity.case_rescale(env, n=1, sizes=(2,))
         env.close()
+
+
+def test_decrypt_level(emu_lib):
+    parity.case_decrypt_level(emu_lib, 2048, n=20)
