@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -180,6 +181,7 @@ static Mod make_mod(u64 q, u64 N)
     Mod m{};
     m.q = q;
     m.two_q = 2 * q;
+    m.nq = 0 - q;
     m.bits = (u32)hm::bitlen(q);
     m.sh = m.bits - 2;
     m.mu = (u64)((((hm::u128)1) << (62 + m.bits)) / q);
@@ -187,6 +189,36 @@ static Mod make_mod(u64 q, u64 N)
     m.ninv = hm::invmod(N % q, q);
     m.ninv_s = hm::shoup(m.ninv, q);
     return m;
+}
+
+// Lazy-reduction schedule of the CTA-local transforms for one modulus (see ntt_core.cuh bfly_fwd /
+// bfly_inv).  Values may grow up to Bmax*q <= 2^64 between reductions, Bmax = floor((2^64-1)/q).
+template <int LG> static void lazy_schedule(Mod &m, int c, int L_top)
+{
+    const u64 bmax = ~u64(0) / m.q;
+    const int NP = Sched<LG>::NP;
+    // forward: inputs < 2q, each split pre-stage and each stage adds 2q
+    u64 b = 2 + 2 * (u64)c;
+    m.fwd_mask = 0;
+    for (int P = 0; P < NP; P++) {
+        const u64 K = Sched<LG>::K[P];
+        if (b + 2 * K > bmax) { m.fwd_mask |= 1u << P; b = 2; }
+        if (b + 2 * K > bmax) { m.fwd_mask |= 1u << (8 + P); b = 2 + 2 * (K - K / 2); }
+        else b += 2 * K;
+    }
+    // inverse: canonical inputs (< q); the sum path doubles its bound per stage
+    b = 1;
+    m.inv_mask = 0;
+    for (int P = NP - 1; P >= 0; P--) {
+        const int K = Sched<LG>::K[P];
+        if ((b << K) > bmax) { m.inv_mask |= 1u << P; b = 2; }
+        m.inv_c[P] = (u32)b;
+        if ((b << K) > bmax) { m.inv_mask |= 1u << (8 + P); b = u64(2) << (K - K / 2); }
+        else b <<= K;
+    }
+    // key-switch inner product: every digit adds a Shoup product < 2q to the accumulators
+    const u64 period = bmax >= 4 ? (bmax - 2) / 2 : 1;
+    m.acc_period = (u32)(period > (u64)L_top + 1 ? (u64)L_top + 1 : period);
 }
 
 static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std::vector<u64> &psi)
@@ -199,6 +231,7 @@ static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std
     for (size_t i = 0; i < M; i++) {
         const u64 q = moduli[i];
         c->mods[i] = make_mod(q, N);
+        NTT_DISPATCH(c, lazy_schedule<LG>(c->mods[i], c->c, (int)c->K));
         const u64 ipsi = hm::invmod(psi[i], q);
         u64 p = 1, ip = 1;
         for (size_t k = 0; k < N; k++) {
@@ -249,7 +282,7 @@ template <int LG> static int set_smem_attrs()
     const int bytes = NttCfg<LG>::SMEM_BYTES;
     CK(cudaFuncSetAttribute(k_ntt_fwd<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_ntt_inv<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_ks_inner<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_ks_inner<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_moddown<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 #endif
     return 0;
@@ -290,6 +323,10 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
     c->K = K;
     c->logn = logn;
     c->lognl = logn > 13 ? 13 : logn;
+    if (const char *e = getenv("B200HE_LOGNL")) {   // tuning knob: CTA-local transform size (limb split 2^(logn-lognl) ways, <= 4)
+        const int v = atoi(e);
+        if (v >= 10 && v <= 13 && v <= logn && logn - v <= 2) c->lognl = v;
+    }
     c->c = logn - c->lognl;
     c->t = plain_modulus;
     if (scheme == B200HE_BFV && init_behz(c, mv, pv)) { delete c; return -1; }
@@ -355,15 +392,31 @@ extern "C" int b200he_ctx_set_workspace(b200he_ctx *c, uint64_t bytes)
 // ------------------------------------------------------------------------------------ keys
 static size_t key_words(const b200he_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->N; }
 
+// device layout of a key: [key words | Shoup quotients of the key words]
+static int upload_key(b200he_ctx *c, u64 *d, const uint64_t *key)
+{
+    const size_t words = key_words(c);
+    for (size_t J = 0; J + 1 < c->K; J++)   // residues must be canonical: the Shoup form relies on k < q
+        for (size_t k = 0; k < 2; k++)
+            for (size_t l = 0; l < c->K; l++) {
+                const uint64_t *p = key + ((J * 2 + k) * c->K + l) * c->N, q = c->mods[l].q;
+                for (size_t n = 0; n < c->N; n++)
+                    if (p[n] >= q) return fail("set key: residue out of range (digit %zu, component %zu, limb %zu)", J, k, l);
+            }
+    CK(cudaMemcpyAsync(d, key, words * 8, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, B200HE_KERN_COPY, k_shoup_quotients, blocks_for(words), 256, 0, c->T, d, d + words, (int)c->K, words);
+    LAUNCH_CHECK();
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 extern "C" int b200he_set_relin_key(b200he_ctx *c, const uint64_t *key)
 {
     if (!c || !key) return fail("set_relin_key: NULL argument");
     if (c->K < 2) return fail("set_relin_key: context has no special prime (K < 2)");
     CK(cudaSetDevice(c->device));
-    if (!c->relin) CK(cudaMalloc((void **)&c->relin, key_words(c) * 8));
-    CK(cudaMemcpyAsync(c->relin, key, key_words(c) * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    if (!c->relin) CK(cudaMalloc((void **)&c->relin, 2 * key_words(c) * 8));
+    return upload_key(c, c->relin, key);
 }
 extern "C" int b200he_set_galois_key(b200he_ctx *c, uint32_t elt, const uint64_t *key)
 {
@@ -372,10 +425,8 @@ extern "C" int b200he_set_galois_key(b200he_ctx *c, uint32_t elt, const uint64_t
     if (!(elt & 1) || elt >= 2 * c->N) return fail("set_galois_key: invalid Galois element %u", elt);
     CK(cudaSetDevice(c->device));
     u64 *&d = c->gal[elt];
-    if (!d) CK(cudaMalloc((void **)&d, key_words(c) * 8));
-    CK(cudaMemcpyAsync(d, key, key_words(c) * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    if (!d) CK(cudaMalloc((void **)&d, 2 * key_words(c) * 8));
+    return upload_key(c, d, key);
 }
 extern "C" int b200he_has_galois_key(const b200he_ctx *c, uint32_t elt) { return c && c->gal.count(elt) ? 1 : 0; }
 
@@ -764,13 +815,15 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
         } else {
             A.tcoef = tg; A.tcoef_stride = t_stride; A.target = nullptr; A.target_stride = 0;
         }
-        A.key = key; A.acc = acc; A.L = L; A.K = (int)K;
+        A.key = key; A.key_s = key + key_words(c); A.acc = acc; A.rp = rp; A.L = L; A.K = (int)K; A.B = (int)nb;
         NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_KS_INNER, k_ks_inner<LG>, (unsigned)((nb * (L + 1)) << c->c), NttCfg<LG>::THREADS,
-                               NttCfg<LG>::SMEM_BYTES, c->T, A, c->c));
+                               KsCfg<LG>::SMEM_BYTES, c->T, A, c->c));
         if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: k_ks_inner launch failed"); break; }
-        // rounded special-prime limb in coefficient form
-        rc = ntt_inv(c, acc + (size_t)L * N, rp, nb * 2, (size_t)(L + 1) * N, N, 1, (int)K - 1, INV_ADDHALF);
-        if (rc) break;
+        // rounded special-prime limb in coefficient form: fused into k_ks_inner for unsplit limbs
+        if (c->c > 0) {
+            rc = ntt_inv(c, acc + (size_t)L * N, rp, nb * 2, (size_t)(L + 1) * N, N, 1, (int)K - 1, INV_ADDHALF);
+            if (rc) break;
+        }
         ModDownArgs D{};
         D.rp = rp; D.base = acc; D.base_ct_stride = w_acc; D.base_poly_stride = (size_t)(L + 1) * N;
         D.addend[0] = add0 ? add0 + b0 * add_stride : nullptr;

@@ -53,11 +53,20 @@ struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_l
     __device__ __forceinline__ u64 operator()(u64 v) const { return reduce64(v, m) + fix; }
 };
 
+// lazy Cooley-Tukey butterfly used by the split pre-stages (bound of both outputs: bound(a) + 2q)
+__device__ __forceinline__ void ct_lazy(u64 &a, u64 &b, ulonglong2 w, const Mod &m)
+{
+    const u64 v = shoup_mad(b, w.x, w.y, m.nq, 0);
+    b = a + m.two_q - v;
+    a = a + v;
+}
+
 // Load the pass-0 register layout of local chunk r of a limb split 2^c ways, computing the
 // first c global stages on the fly.  src points at the limb (N_glob coefficients).
+// pre() must return values < 2q; the result is < (2 + 2c) q.
 template <int LOGN, class Pre>
 __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restrict__ src, int c, int r, int tid,
-                                               const ulonglong2 *__restrict__ tw, u64 q, u64 two_q, Pre pre)
+                                               const ulonglong2 *__restrict__ tw, const Mod &m, Pre pre)
 {
     constexpr int NL = 1 << LOGN;
     if (c == 0) {
@@ -71,8 +80,8 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
             ulonglong2 a = ldg2(src + e), b = ldg2(src + e + NL);
             u64 a0 = pre(a.x), a1 = pre(a.y), b0 = pre(b.x), b1 = pre(b.y);
-            ct_bfly(a0, b0, w.x, w.y, q, two_q);
-            ct_bfly(a1, b1, w.x, w.y, q, two_q);
+            ct_lazy(a0, b0, w, m);
+            ct_lazy(a1, b1, w, m);
             x[reg] = r ? b0 : a0;
             x[reg + 1] = r ? b1 : a1;
         });
@@ -83,10 +92,10 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 u64 a0 = pre(h ? v0.y : v0.x), a1 = pre(h ? v1.y : v1.x), a2 = pre(h ? v2.y : v2.x), a3 = pre(h ? v3.y : v3.x);
-                ct_bfly(a0, a2, w1.x, w1.y, q, two_q);
-                ct_bfly(a1, a3, w1.x, w1.y, q, two_q);
+                ct_lazy(a0, a2, w1, m);
+                ct_lazy(a1, a3, w1, m);
                 u64 u = (r >> 1) ? a2 : a0, v = (r >> 1) ? a3 : a1;
-                ct_bfly(u, v, w2.x, w2.y, q, two_q);
+                ct_lazy(u, v, w2, m);
                 x[reg + h] = (r & 1) ? v : u;
             }
         });
@@ -109,12 +118,13 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd(Tables T, con
     const Mod m = T.mods[mid];
     const ulonglong2 *tw = T.tw + (size_t)mid * T.N;
     u64 x[16];
-    load_fwd_split<LOGN>(x, src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N, c, r, tid, tw, m.q, m.two_q, PreNone());
-    ntt_fwd_regs_split<LOGN>(x, sm, tw, m.q, m.two_q, tid, c, r);
+    TwRegs<LOGN, 0> t0;
+    load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
+    load_fwd_split<LOGN>(x, src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N, c, r, tid, tw, m, PreNone());
+    ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
-    for_pairs_contig(tid, [&](int reg, int e) {
-        st2(out + e, csub(csub(x[reg], m.two_q), m.q), csub(csub(x[reg + 1], m.two_q), m.q));
-    });
+    canon_all(x, m);
+    for_pairs_contig(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
 }
 
 // ------------------------------------------------------------------------------------ K2
@@ -139,6 +149,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     const ulonglong2 *itw = T.itw + (size_t)mid * T.N;
     const u64 *in = src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     u64 x[16];
+    TwRegs<LOGN, Sched<LOGN>::NP - 1> tl;
+    load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, (1 << c) + r);
     for_pairs_contig(tid, [&](int reg, int e) {
         ulonglong2 v = ldg2(in + e);
         x[reg] = v.x;
@@ -146,10 +158,11 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     });
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     if (c == 0) {
-        ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0);
+        ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0, tl);
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, mode), inv_finish(x[reg + 1], m, mode)); });
     } else {
-        ntt_inv_regs_split<LOGN, false>(x, sm, itw, m, tid, c, r);
+        ntt_inv_regs_split<LOGN, false>(x, sm, itw, m, tid, c, r, tl);
+        reduce_all(x, m);
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
     }
 }
@@ -195,31 +208,52 @@ __global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict_
 // ------------------------------------------------------------------------------------ K6 step 2
 // acc[b][k][I] = sum_J NTT_{q_I}(t[b][J] mod q_I) (.) key[J][k][I]      (I == L  <->  special prime)
 // CKKS: the I == J term reuses the NTT-form target.  grid = B * (L+1) << c.
+//
+// One CTA owns (ciphertext b, output modulus I[, chunk r]) and loops over the L digits: the digit is
+// lifted and transformed in registers, then multiplied into both key components.  The keys carry
+// their Shoup quotients (key_s, computed once at upload by k_shoup_quotients), so a multiply-
+// accumulate is one shoup_mad -- 10 integer multiply-adds, valid for ANY 64-bit digit value (the
+// transform output needs no reduction) -- and the accumulators stay lazy (Mod::acc_period).  The two
+// accumulator limbs live in shared memory between digits ([p][tid] pairs, conflict-free 128-bit
+// accesses) so the transform has the whole register file.
+// Unsplit limbs (c == 0): the CTA of the special prime finishes with the inverse transform and the
+// "+ q_sp/2" rounding of its two accumulators and writes them straight to rp (the input of
+// k_moddown); that limb never goes to HBM in NTT form.
 struct KsInnerArgs {
     const u64 *tcoef;      // target in coefficient form: tcoef + b*tcoef_stride + J*N
     size_t tcoef_stride;
     const u64 *target;     // NTT-form target (CKKS) or nullptr (BFV): target + b*target_stride + J*N
     size_t target_stride;
     const u64 *key;        // [Ltop][2][K][N]
+    const u64 *key_s;      // Shoup quotients of key, same layout
     u64 *acc;              // [B][2][L+1][N]
-    int L, K;
+    u64 *rp;               // [B][2][N]: rounded special-prime limb in coefficient form (written when c == 0)
+    int L, K, B;           // B = ciphertexts in this launch
+};
+template <int LOGN> struct KsCfg {
+    static constexpr int SMEM_BYTES = 3 * NttCfg<LOGN>::SMEM_BYTES;   // transform buffer + 2 accumulator limbs
 };
 template <int LOGN>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T, KsInnerArgs A, int c)
 {
-    constexpr int NL = 1 << LOGN;
+    constexpr int NL = 1 << LOGN, TH = NttCfg<LOGN>::THREADS;
     u64 *sm = dyn_smem();
+    u64 *acc_sm[2] = { sm + NL, sm + 2 * NL };
     const int tid = threadIdx.x;
     const int r = blockIdx.x & ((1 << c) - 1);
     const int unit = blockIdx.x >> c;
-    const int L = A.L, b = unit / (L + 1), I = unit % (L + 1);
+    // the special-prime units (longest: they also run the fused inverse transforms) are scheduled first
+    const int L = A.L;
+    const int b = unit < A.B ? unit : (unit - A.B) / L, I = unit < A.B ? L : (unit - A.B) % L;
     const int ki = (I == L) ? A.K - 1 : I;
     const Mod m = T.mods[ki];
     const ulonglong2 *tw = T.tw + (size_t)ki * T.N;
     const size_t N = T.N, off = (size_t)r * NL;
-    u64 a0[16], a1[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) a0[i] = a1[i] = 0;
+    for (int p = 0; p < 8; p++) {
+        st2(acc_sm[0] + (p * TH + tid) * 2, 0, 0);
+        st2(acc_sm[1] + (p * TH + tid) * 2, 0, 0);
+    }
     for (int J = 0; J < L; J++) {
         u64 x[16];
         if (A.target && I == J) {
@@ -231,31 +265,91 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
             });
         } else {
             const u64 *tp = A.tcoef + (size_t)b * A.tcoef_stride + (size_t)J * N;
+            TwRegs<LOGN, 0> t0;
+            load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
             if (T.mods[J].q > m.q)
-                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m.q, m.two_q, PreReduce{ m });
+                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m, PreReduce{ m });
             else
-                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m.q, m.two_q, PreNone());
-            ntt_fwd_regs_split<LOGN>(x, sm, tw, m.q, m.two_q, tid, c, r);
-#pragma unroll
-            for (int i = 0; i < 16; i++) x[i] = csub(csub(x[i], m.two_q), m.q);
-            __syncthreads();   // shared buffer is reused by the next digit
+                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m, PreNone());
+            ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
         }
-        const u64 *k0 = A.key + (((size_t)J * 2 + 0) * A.K + ki) * N + off;
-        const u64 *k1 = A.key + (((size_t)J * 2 + 1) * A.K + ki) * N + off;
+        const bool fold = ((J + 1) % (int)m.acc_period) == 0;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const size_t koff = (((size_t)J * 2 + k) * A.K + ki) * N + off + 16 * tid;
+            const u64 *kp = A.key + koff, *ksp = A.key_s + koff;
+            ulonglong2 kv[8], ks[8], a[8];
+#pragma unroll
+            for (int p = 0; p < 8; p++) {   // all 16 key loads in flight before the first use
+                kv[p] = ldg2(kp + 2 * p);
+                ks[p] = ldg2(ksp + 2 * p);
+            }
+#pragma unroll
+            for (int p = 0; p < 8; p++) a[p] = ld2(acc_sm[k] + (p * TH + tid) * 2);
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                a[p].x = shoup_mad(x[2 * p], kv[p].x, ks[p].x, m.nq, a[p].x);
+                a[p].y = shoup_mad(x[2 * p + 1], kv[p].y, ks[p].y, m.nq, a[p].y);
+            }
+            if (fold) {
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    a[p].x = reduce_lazy(a[p].x, m);
+                    a[p].y = reduce_lazy(a[p].y, m);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 8; p++) st2(acc_sm[k] + (p * TH + tid) * 2, a[p].x, a[p].y);
+        }
+        __syncthreads();   // the transform buffer is reused by the next digit
+    }
+    if (c == 0 && I == L) {
+        const ulonglong2 *itw = T.itw + (size_t)ki * T.N;
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            u64 x[16];
+            TwRegs<LOGN, Sched<LOGN>::NP - 1> tl;
+            load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, 1);
+            for_pairs_contig(tid, [&](int reg, int e) {
+                const ulonglong2 a = ld2(acc_sm[k] + ((reg >> 1) * TH + tid) * 2);
+                x[reg] = reduce_full(a.x, m);
+                x[reg + 1] = reduce_full(a.y, m);
+            });
+            ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0, tl);
+            u64 *out = A.rp + ((size_t)b * 2 + k) * N;
+            for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, INV_ADDHALF), inv_finish(x[reg + 1], m, INV_ADDHALF)); });
+            __syncthreads();
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        u64 *o = A.acc + (((size_t)b * 2 + k) * (L + 1) + I) * N + off;
         for_pairs_contig(tid, [&](int reg, int e) {
-            ulonglong2 v0 = ldg2(k0 + e), v1 = ldg2(k1 + e);
-            a0[reg] = mad_mod(x[reg], v0.x, a0[reg], m);
-            a0[reg + 1] = mad_mod(x[reg + 1], v0.y, a0[reg + 1], m);
-            a1[reg] = mad_mod(x[reg], v1.x, a1[reg], m);
-            a1[reg + 1] = mad_mod(x[reg + 1], v1.y, a1[reg + 1], m);
+            const ulonglong2 a = ld2(acc_sm[k] + ((reg >> 1) * TH + tid) * 2);
+            st2(o + e, reduce_full(a.x, m), reduce_full(a.y, m));
         });
     }
-    u64 *o0 = A.acc + (((size_t)b * 2 + 0) * (L + 1) + I) * N + off;
-    u64 *o1 = A.acc + (((size_t)b * 2 + 1) * (L + 1) + I) * N + off;
-    for_pairs_contig(tid, [&](int reg, int e) {
-        st2(o0 + e, a0[reg], a0[reg + 1]);
-        st2(o1 + e, a1[reg], a1[reg + 1]);
-    });
+}
+
+// Shoup quotients floor(k * 2^64 / q) of a key-switching key [Ltop][2][K][N], once per upload
+// (restoring division, 64 steps: k < q < 2^61 so the running remainder never overflows).
+__global__ void __launch_bounds__(256) k_shoup_quotients(Tables T, const u64 *__restrict__ key, u64 *__restrict__ key_s, int K, size_t words)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= words) return;
+    const u64 q = T.mods[(gid / T.N) % K].q;
+    u64 rem = key[gid], quot = 0;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        rem <<= 1;
+        quot <<= 1;
+        if (rem >= q) {
+            rem -= q;
+            quot |= 1;
+        }
+    }
+    key_s[gid] = quot;
 }
 
 // ------------------------------------------------------------------------------------ K6 step 3 / K9
@@ -292,14 +386,17 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
     const u64 fix = m.q - T.halfmod[(size_t)A.x * T.M + j];
     const ulonglong2 qi = T.qinv[(size_t)A.x * T.M + j];
     u64 x[16];
-    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m.q, m.two_q, PreReduceFix{ m, fix });
-    ntt_fwd_regs_split<LOGN>(x, sm, tw, m.q, m.two_q, tid, c, r);
+    TwRegs<LOGN, 0> t0;
+    load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
+    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m, fix });
+    ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     const u64 *bp = A.base + (size_t)b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + off;
     const u64 *ap = A.addend[p] ? A.addend[p] + (size_t)b * A.add_ct_stride + (size_t)j * N + off : nullptr;
     u64 *op = A.out + (size_t)b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + off;
+    canon_all(x, m);
     for_pairs_contig(tid, [&](int reg, int e) {
         ulonglong2 bv = ldg2(bp + e);
-        u64 u0 = csub(csub(x[reg], m.two_q), m.q), u1 = csub(csub(x[reg + 1], m.two_q), m.q);
+        u64 u0 = x[reg], u1 = x[reg + 1];
         u64 v0 = shoup(sub_mod(bv.x, u0, m.q), qi.x, qi.y, m.q);
         u64 v1 = shoup(sub_mod(bv.y, u1, m.q), qi.x, qi.y, m.q);
         if (ap) {

@@ -26,12 +26,20 @@ typedef uint32_t u32;
 struct Mod {
     u64 q;        // the prime
     u64 two_q;    // 2q
+    u64 nq;       // 2^64 - q   ("+ k*nq" subtracts k*q in 64-bit wrap-around arithmetic)
     u64 mu;       // floor(2^(62+bits) / q)  -- shift-Barrett constant, < 2^63
     u64 r64;      // floor(2^64 / q)         -- single-word Barrett (SEAL const_ratio[1])
     u64 ninv;     // N^{-1} mod q
     u64 ninv_s;   // Shoup quotient of ninv
     u32 bits;     // bit length of q
     u32 sh;       // bits - 2
+    // Lazy-reduction schedule of the CTA-local transforms (built on the host from the pass schedule and
+    // floor(2^64/q), see build_tables): bit P = reduce all coefficients to [0,2q) before pass P,
+    // bit 8+P = reduce again after the first K/2 stages of pass P.
+    u32 fwd_mask, inv_mask;
+    u32 inv_c[4];   // inverse: bound multiplier C (values < C*q) at the start of pass P
+    u32 acc_period; // key-switch inner product: reduce the lazy accumulators every acc_period digits
+    u32 pad_;
 };
 
 __host__ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b)
@@ -55,6 +63,29 @@ __host__ __device__ __forceinline__ u64 shoup_lazy(u64 y, u64 w, u64 ws, u64 q)
     return y * w - mulhi64(y, ws) * q;
 }
 __host__ __device__ __forceinline__ u64 shoup(u64 y, u64 w, u64 ws, u64 q) { return csub(shoup_lazy(y, w, ws, q), q); }
+
+// w*y (+ x) with the Shoup quotient: x + (w*y mod q) + {0,q}, all in 64-bit wrap-around arithmetic.
+// 10 integer multiply-adds: 4 for the high product, 6 for the two low products (the subtraction of
+// qhat*q is folded into the multiply-add chain through nq = 2^64 - q).
+__host__ __device__ __forceinline__ u64 shoup_mad(u64 y, u64 w, u64 ws, u64 nq, u64 x)
+{
+    return y * w + mulhi64(y, ws) * nq + x;
+}
+// any 64-bit x -> x mod q + {0,q}  (in [0,2q)).  NARROW: floor(2^64/q) fits 32 bits (q > 2^32), then
+// the quotient costs 2 multiply-adds instead of 4.  Callers branch once per CTA on Mod::bits.
+template <bool NARROW> __host__ __device__ __forceinline__ u64 reduce_lazy_t(u64 x, const Mod &m)
+{
+    if (NARROW) {
+        const u32 r = (u32)m.r64, x0 = (u32)x, x1 = (u32)(x >> 32);
+        const u64 t = (u64)x0 * r;
+        const u64 u = (u64)x1 * r + (t >> 32);
+        return x + (u >> 32) * m.nq;
+    }
+    return x + mulhi64(x, m.r64) * m.nq;
+}
+__host__ __device__ __forceinline__ u64 reduce_lazy(u64 x, const Mod &m) { return m.bits > 32 ? reduce_lazy_t<true>(x, m) : reduce_lazy_t<false>(x, m); }
+// any 64-bit x -> canonical x mod q
+__host__ __device__ __forceinline__ u64 reduce_full(u64 x, const Mod &m) { return csub(reduce_lazy(x, m), m.q); }
 
 // x mod q for any 64-bit x (SEAL barrett_reduce_64)
 __host__ __device__ __forceinline__ u64 reduce64(u64 x, const Mod &m)

@@ -107,97 +107,205 @@ __device__ __forceinline__ ulonglong2 ld_tw(const ulonglong2 *p)
 #endif
 }
 
-// ---- butterflies of pass P on the 16 registers ----
+// ---- barrier for the exchange between pass P and pass P+1 (either direction) ----
+// After stage S_P the transform has split into independent blocks of BLK_P = N >> S_P coefficients,
+// so the registers a pass-(P+1) thread picks up were written by the BLK_P/16 threads that own the
+// enclosing pass-P block: only those need to meet.  For N = 8192 that is one CTA-wide barrier, one
+// 64-thread named barrier and one __syncwarp per transform instead of three CTA-wide barriers.
+template <int LOGN, int P> __device__ __forceinline__ void xchg_sync(int tid)
+{
+    constexpr int GROUP = (Pass<LOGN, P>::BLK) / 16;
+#ifdef B200HE_EMU
+    (void)tid;
+    __syncthreads();
+#else
+    if constexpr (GROUP >= NttCfg<LOGN>::THREADS) __syncthreads();
+    else if constexpr (GROUP <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / GROUP), "r"(GROUP) : "memory");
+#endif
+}
+
+// ---- twiddles of one pass, fetched into registers ahead of the exchange that precedes the pass ----
 // `pre` = 2^c + r selects local chunk r of a limb split 2^c ways (pre = 1: unsplit): local stage
 // S+u of chunk r is global stage c+S+u, whose twiddle index is (pre << (S+u)) + local block index.
-template <int LOGN, int P> __device__ __forceinline__ void bfly_fwd(u64 (&x)[16], const ulonglong2 *__restrict__ tw, u64 q, u64 two_q, int tid, int pre)
+template <int LOGN, int P> struct TwRegs { ulonglong2 w[(1 << Pass<LOGN, P>::K) - 1]; };
+
+// Stages [U0, U1) of pass P.  A 4-stage pass needs 15 twiddles (60 registers): the stages executed first
+// are fetched ahead of the exchange (load_tw_early), the rest once the first stage has retired
+// (load_tw_late) so that the transform fits the 128-register budget of a 512-thread CTA.
+template <int LOGN, int P, int U0, int U1>
+__device__ __forceinline__ void load_tw_range(TwRegs<LOGN, P> &t, const ulonglong2 *__restrict__ tw, int tid, int pre)
 {
     typedef Pass<LOGN, P> G;
     const int hi = G::hi(tid);
 #pragma unroll
+    for (int u = U0; u < U1; u++)
+#pragma unroll
+        for (int blk = 0; blk < (1 << u); blk++) t.w[(1 << u) - 1 + blk] = ld_tw(tw + (pre << (G::S + u)) + (hi << u) + blk);
+}
+template <int K> struct TwSplit {
+    static constexpr int FWD_EARLY_END = K <= 3 ? K : 3;      // forward runs u = 0..K-1
+    static constexpr int INV_EARLY_BEGIN = K <= 3 ? 0 : K - 1;   // inverse runs u = K-1..0
+};
+template <int LOGN, int P, bool INVERSE> __device__ __forceinline__ void load_tw_early(TwRegs<LOGN, P> &t, const ulonglong2 *__restrict__ tw, int tid, int pre)
+{
+    constexpr int K = Pass<LOGN, P>::K;
+    if constexpr (INVERSE) load_tw_range<LOGN, P, TwSplit<K>::INV_EARLY_BEGIN, K>(t, tw, tid, pre);
+    else load_tw_range<LOGN, P, 0, TwSplit<K>::FWD_EARLY_END>(t, tw, tid, pre);
+}
+template <int LOGN, int P, bool INVERSE> __device__ __forceinline__ void load_tw_late(TwRegs<LOGN, P> &t, const ulonglong2 *__restrict__ tw, int tid, int pre)
+{
+    constexpr int K = Pass<LOGN, P>::K;
+    if constexpr (INVERSE) load_tw_range<LOGN, P, 0, TwSplit<K>::INV_EARLY_BEGIN>(t, tw, tid, pre);
+    else load_tw_range<LOGN, P, TwSplit<K>::FWD_EARLY_END, K>(t, tw, tid, pre);
+}
+
+__device__ __forceinline__ void reduce_all(u64 (&x)[16], const Mod &m)
+{
+    if (m.bits > 32) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = reduce_lazy_t<true>(x[i], m);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = reduce_lazy_t<false>(x[i], m);
+    }
+}
+// all 16 registers -> canonical residues
+__device__ __forceinline__ void canon_all(u64 (&x)[16], const Mod &m)
+{
+    reduce_all(x, m);
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = csub(x[i], m.q);
+}
+
+// ---- butterflies of pass P on the 16 registers ----
+// Lazy Cooley-Tukey: X = x + w*y, Y = x - w*y + 2q with w*y in [0,2q) from the Shoup product, which
+// accepts ANY 64-bit y.  Nothing is reduced per butterfly: the bound of every value grows by 2q per
+// stage and the host-built schedule (Mod::fwd_mask) says where a pass must first pull the registers
+// back to [0,2q) so that nothing reaches 2^64.
+template <int LOGN, int P>
+__device__ __forceinline__ void bfly_fwd(u64 (&x)[16], TwRegs<LOGN, P> &t, const Mod &m, const ulonglong2 *__restrict__ tw, int tid, int pre)
+{
+    typedef Pass<LOGN, P> G;
+    if ((m.fwd_mask >> P) & 1) reduce_all(x, m);
+    const bool mid = (m.fwd_mask >> (8 + P)) & 1;
+    const u64 nq = m.nq, two_q = m.two_q;
+#pragma unroll
     for (int u = 0; u < G::K; u++) {
+        if (u == 1) load_tw_late<LOGN, P, false>(t, tw, tid, pre);
+        if (u == G::K / 2 && mid) reduce_all(x, m);
         const int half = 1 << (G::K - 1 - u);
 #pragma unroll
         for (int blk = 0; blk < (1 << u); blk++) {
-            const ulonglong2 w = ld_tw(tw + (pre << (G::S + u)) + (hi << u) + blk);
+            const ulonglong2 w = t.w[(1 << u) - 1 + blk];
 #pragma unroll
             for (int jj = 0; jj < half; jj++) {
                 const int j0 = blk * 2 * half + jj, j1 = j0 + half;
 #pragma unroll
-                for (int c = 0; c < G::C; c++) ct_bfly(x[j0 * G::C + c], x[j1 * G::C + c], w.x, w.y, q, two_q);
+                for (int c = 0; c < G::C; c++) {
+                    u64 &a = x[j0 * G::C + c], &b = x[j1 * G::C + c];
+                    const u64 v = shoup_mad(b, w.x, w.y, nq, 0);
+                    b = a + two_q - v;
+                    a = a + v;
+                }
             }
         }
     }
 }
 
-// FINAL: this pass contains global stage 0, into which N^{-1} is folded
-// (itw[0] holds (w1^{-1} * N^{-1}, shoup) for that purpose).
+// Lazy Gentleman-Sande: X = x + y, Y = w*(x - y + C q) where C q bounds y; the Shoup product brings Y
+// back to [0,2q) while the X path doubles its bound per stage (schedule: Mod::inv_mask / inv_c).
+// FINAL: this pass ends with global stage 0, into which N^{-1} is folded
+// (itw[0] holds (w1^{-1} * N^{-1}, shoup) for that purpose); outputs are then in [0,2q).
 template <int LOGN, int P, bool FINAL>
-__device__ __forceinline__ void bfly_inv(u64 (&x)[16], const ulonglong2 *__restrict__ itw, const Mod &m, int tid, int pre)
+__device__ __forceinline__ void bfly_inv(u64 (&x)[16], TwRegs<LOGN, P> &t, const Mod &m, ulonglong2 wfold, const ulonglong2 *__restrict__ itw, int tid, int pre)
 {
     typedef Pass<LOGN, P> G;
-    const int hi = G::hi(tid);
-    const u64 q = m.q, two_q = m.two_q;
-    constexpr bool FOLD = FINAL && P == 0;   // this pass ends with global stage 0
+    constexpr bool FOLD = FINAL && P == 0;
+    if ((m.inv_mask >> P) & 1) reduce_all(x, m);
+    const bool mid = (m.inv_mask >> (8 + P)) & 1;
+    const u64 nq = m.nq;
+    u64 cq = m.q * m.inv_c[P];
 #pragma unroll
     for (int u = G::K - 1; u >= (FOLD ? 1 : 0); u--) {
+        if (u == G::K - 2) load_tw_late<LOGN, P, true>(t, itw, tid, pre);
+        if (G::K - 1 - u == G::K / 2 && mid) {
+            reduce_all(x, m);
+            cq = m.two_q;
+        }
         const int half = 1 << (G::K - 1 - u);
 #pragma unroll
         for (int blk = 0; blk < (1 << u); blk++) {
-            const ulonglong2 w = ld_tw(itw + (pre << (G::S + u)) + (hi << u) + blk);
+            const ulonglong2 w = t.w[(1 << u) - 1 + blk];
 #pragma unroll
             for (int jj = 0; jj < half; jj++) {
                 const int j0 = blk * 2 * half + jj, j1 = j0 + half;
 #pragma unroll
-                for (int c = 0; c < G::C; c++) gs_bfly(x[j0 * G::C + c], x[j1 * G::C + c], w.x, w.y, q, two_q);
+                for (int c = 0; c < G::C; c++) {
+                    u64 &a = x[j0 * G::C + c], &b = x[j1 * G::C + c];
+                    const u64 d = a + cq - b;
+                    a = a + b;
+                    b = shoup_mad(d, w.x, w.y, nq, 0);
+                }
             }
         }
+        cq += cq;
     }
     if constexpr (FOLD) {
-        const ulonglong2 w = ld_tw(itw);
+        if (G::K - 1 == G::K / 2 && mid) {
+            reduce_all(x, m);
+            cq = m.two_q;
+        }
         constexpr int half = 1 << (G::K - 1);
 #pragma unroll
         for (int jj = 0; jj < half; jj++)
 #pragma unroll
             for (int c = 0; c < G::C; c++) {
                 u64 &a = x[jj * G::C + c], &b = x[(jj + half) * G::C + c];
-                const u64 s = a + b, d = a - b + two_q;
-                a = shoup_lazy(s, m.ninv, m.ninv_s, q);
-                b = shoup_lazy(d, w.x, w.y, q);
+                const u64 s = a + b, d = a + cq - b;
+                a = shoup_mad(s, m.ninv, m.ninv_s, nq, 0);
+                b = shoup_mad(d, wfold.x, wfold.y, nq, 0);
             }
     }
 }
 
-// Forward transform of local chunk r (of 2^c).  In: x in pass-0 layout (Pass<LOGN,0>::elem),
-// values < 4q.  Out: x in the contiguous layout (local coefficient 16*tid + j in x[j]), [0,4q).
+// Forward transform of local chunk r (of 2^c).  In: x in pass-0 layout (Pass<LOGN,0>::elem), values
+// < 2q (+2q per split pre-stage); t = the pass-0 twiddles (load_tw_early<LOGN,0,false>, issued by the caller next
+// to its data loads).  Out: x in the contiguous layout (local coefficient 16*tid + j in x[j]), lazy
+// (any value < 2^64 congruent to the result: finish with reduce_full).
 // Uses sm (2^LOGN words).  Caller must __syncthreads() before reusing sm for another transform.
 template <int LOGN, int P = 0>
-__device__ __forceinline__ void ntt_fwd_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ tw, u64 q, u64 two_q, int tid, int c, int r)
+__device__ __forceinline__ void ntt_fwd_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ tw, const Mod &m, int tid, int c, int r,
+                                                   TwRegs<LOGN, P> &t)
 {
-    if constexpr (P > 0) {
-        __syncthreads();
-        smem_xfer<LOGN, P, false>(x, sm, tid);
-    }
-    bfly_fwd<LOGN, P>(x, tw, q, two_q, tid, (1 << c) + r);
+    bfly_fwd<LOGN, P>(x, t, m, tw, tid, (1 << c) + r);
     if constexpr (P + 1 < Sched<LOGN>::NP) {
+        TwRegs<LOGN, P + 1> tn;
+        load_tw_early<LOGN, P + 1, false>(tn, tw, tid, (1 << c) + r);
         smem_xfer<LOGN, P, true>(x, sm, tid);
-        ntt_fwd_regs_split<LOGN, P + 1>(x, sm, tw, q, two_q, tid, c, r);
+        xchg_sync<LOGN, P>(tid);
+        smem_xfer<LOGN, P + 1, false>(x, sm, tid);
+        ntt_fwd_regs_split<LOGN, P + 1>(x, sm, tw, m, tid, c, r, tn);
     }
 }
 
-// Inverse transform of local chunk r.  In: x in the contiguous layout, values < 2q.
-// Out: x in pass-0 layout, [0,2q); FINAL (unsplit limb): already multiplied by N^{-1}.
+// Inverse transform of local chunk r.  In: x in the contiguous layout, canonical values (< q);
+// t = twiddles of the last pass (load_tw_early<LOGN,NP-1,true> on the inverse table).
+// Out: x in pass-0 layout; FINAL (unsplit limb): multiplied by N^{-1}, in [0,2q); otherwise lazy.
 template <int LOGN, bool FINAL, int P = Sched<LOGN>::NP - 1>
-__device__ __forceinline__ void ntt_inv_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ itw, const Mod &m, int tid, int c, int r)
+__device__ __forceinline__ void ntt_inv_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ itw, const Mod &m, int tid, int c, int r,
+                                                   TwRegs<LOGN, P> &t)
 {
-    if constexpr (P + 1 < Sched<LOGN>::NP) {
-        __syncthreads();
-        smem_xfer<LOGN, P, false>(x, sm, tid);
-    }
-    bfly_inv<LOGN, P, FINAL>(x, itw, m, tid, (1 << c) + r);
+    ulonglong2 wfold = make_ulonglong2(0, 0);
+    if constexpr (FINAL && P == 0) wfold = ld_tw(itw);
+    bfly_inv<LOGN, P, FINAL>(x, t, m, wfold, itw, tid, (1 << c) + r);
     if constexpr (P > 0) {
+        TwRegs<LOGN, P - 1> tn;
+        load_tw_early<LOGN, P - 1, true>(tn, itw, tid, (1 << c) + r);
         smem_xfer<LOGN, P, true>(x, sm, tid);
-        ntt_inv_regs_split<LOGN, FINAL, P - 1>(x, sm, itw, m, tid, c, r);
+        xchg_sync<LOGN, P - 1>(tid);
+        smem_xfer<LOGN, P - 1, false>(x, sm, tid);
+        ntt_inv_regs_split<LOGN, FINAL, P - 1>(x, sm, itw, m, tid, c, r, tn);
     }
 }
 
