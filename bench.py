@@ -47,28 +47,54 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
-
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region (NVML; nvidia-smi as a fallback)"""
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.stop = gpu, [], threading.Event()
+        self.gpu, self.sm, self.mx, self.reasons, self.stop = gpu, [], None, set(), threading.Event()
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.n = 0
 
     def run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while True:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+                self.n += 1
+                if self.stop.wait(0.002):
+                    break
+        except Exception:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            while True:
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    r = [x.strip() for x in out.split(",")]
+                    self.sm.append(int(r[0]))
+                    self.mx = int(r[1])
+                    self.reasons |= {names[i] for i in range(4) if r[2 + i].lower().startswith("active")}
+                    self.n += 1
+                except Exception:
+                    pass
+                if self.stop.wait(0.05):
+                    break
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.01)
         return self
 
     def __exit__(self, *a):
@@ -76,12 +102,8 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": self.n}
 
 
 def synth_inputs(moduli, n, L, N, seed):
@@ -154,10 +176,32 @@ def run_b200(args):
         ctx.relinearize(R, out=R)
         ctx.rescale_to_next(R, out=R)
 
+    # end-to-end leg: the batch is cut into chunks that travel through E2E_STREAMS contexts (one stream each), so
+    # the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap on the PCIe/compute engines
+    E2E_STREAMS, CHUNK = 3, 125
+    e2e = []
+    for i in range(E2E_STREAMS):
+        cx = hb.Context(CKKS, N_POLY, host.moduli, host.psi, 0, device=local)
+        st = torch.cuda.Stream(device=local)
+        cx.set_stream(st.cuda_stream)
+        cx.set_relin_key(host.relin_key())
+        bufs = [hb.Batch(cx), hb.Batch(cx), hb.Batch(cx)]
+        bufs[0].resize(CHUNK, 2, L, True, scale)
+        bufs[1].resize(CHUNK, 2, L, True, scale)
+        e2e.append((cx, st, bufs))
+
     def e2e_step():
-        upload()
-        step()
-        R.download_to(out_pin.data_ptr(), 0, BATCH)   # blocks until the results are on the host
+        for k, first in enumerate(range(0, BATCH, CHUNK)):
+            cx, st, (ca, cb, cr) = e2e[k % E2E_STREAMS]
+            n = min(CHUNK, BATCH - first)
+            ca.upload_from(a_pin.data_ptr() + first * words_in * 8, 0, n)
+            cb.upload_from(b_pin.data_ptr() + first * words_in * 8, 0, n)
+            cx.multiply(ca, cb, n=n, out=cr)
+            cx.relinearize(cr, out=cr)
+            cx.rescale_to_next(cr, out=cr)
+            cr.download_to(out_pin.data_ptr() + first * words_out * 8, 0, n, wait=False)
+        for cx, st, _ in e2e:
+            cx.sync()   # results are on the host
 
     def barrier():
         if dist is not None:
@@ -193,16 +237,23 @@ def run_b200(args):
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = clk.summary()
 
-    # ---- end to end through the C ABI with host buffers (pinned): H2D + compute + D2H per step
+    # ---- end to end through the C ABI with host buffers (pinned): H2D + compute + D2H per step.  Several streams
+    # are involved, so the region is bracketed by events on the default stream that every stream joins.
     for _ in range(2):
         e2e_step()
     barrier()
-    ev0.record(stream)
+    main = torch.cuda.current_stream()
+    ev0.record(main)
+    for _, st, _b in e2e:
+        st.wait_event(ev0)
     for _ in range(args.steps):
         e2e_step()
-    ev1.record(stream)
+    for _, st, _b in e2e:
+        main.wait_stream(st)
+    ev1.record(main)
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e_launches = sum(cx.launch_count() for cx, _, _b in e2e)
 
     # sanity: the timed path produced the bits the step defines (first result vs a fresh single-ciphertext run)
     chk = ctx.multiply(ctx.batch(a_np[:1], scale=scale), ctx.batch(b_np[:1], scale=scale))
@@ -235,7 +286,8 @@ def run_b200(args):
         "dtype": "u64", "data": "synthetic (uniform random residues, seed 1234; real relinearization key)",
         "config": CONFIG, "clocks": clocks,
         "e2e": {"value": samples / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * words_in * 8,
-                "d2h_bytes_per_step": BATCH * words_out * 8, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": BATCH * words_out * 8, "ms_per_step": e2e_ms / args.steps,
+                "pipeline": f"{E2E_STREAMS} streams x chunks of {CHUNK} ciphertext pairs"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,

@@ -69,6 +69,8 @@ void b200he_batch_destroy(b200he_batch *b);
 int b200he_batch_resize(b200he_batch *b, uint64_t count, int size, int L, int ntt_form, double scale);
 int b200he_batch_upload(b200he_batch *b, uint64_t first, uint64_t n, const uint64_t *host);
 int b200he_batch_download(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host);
+/* same without the wait: `host` (pinned memory) is valid after the next b200he_ctx_sync */
+int b200he_batch_download_async(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host);
 uint64_t b200he_batch_count(const b200he_batch *b);
 int b200he_batch_size(const b200he_batch *b);
 int b200he_batch_level(const b200he_batch *b);      /* L = number of RNS limbs */
@@ -95,6 +97,13 @@ int b200he_relinearize(b200he_ctx *ctx, const b200he_batch *in, b200he_batch *ou
 /* Evaluator::rotate_vector / rotate_rows with SEAL's NAF fallback when no key exists for the step
  * R/src/engine/seal_context.cpp:302,337,378, R/src/benchmarks/ckks/seal_ckks_matmult_row_benchmark.cpp:507  (out may alias in) */
 int b200he_rotate(b200he_ctx *ctx, const b200he_batch *in, int step, b200he_batch *out);
+/* per-ciphertext rotation steps: out[i] = rotate_vector(in[i], steps[i]) with SEAL's NAF decomposition per
+ * ciphertext; ciphertexts sharing a power-of-two term are key-switched together.
+ * R/src/engine/seal_context.cpp:378 (collapseCKKS rotates sample i by -i)  (out may alias in) */
+int b200he_rotate_each(b200he_ctx *ctx, const b200he_batch *in, const int32_t *steps, b200he_batch *out);
+/* out (one ciphertext) = sum over the batch: the mutex-guarded add_inplace reduction of
+ * R/src/engine/seal_context.cpp:397-400 */
+int b200he_sum(b200he_ctx *ctx, const b200he_batch *in, b200he_batch *out);
 /* Evaluator::rotate_columns_inplace (BFV) / complex_conjugate (CKKS): Galois element 2N-1
  * R/src/engine/seal_context.cpp:308 */
 int b200he_rotate_columns(b200he_ctx *ctx, const b200he_batch *in, b200he_batch *out);

@@ -1,0 +1,224 @@
+// b200_benchmarks.h -- the 11 HEBench workload classes of the B200 backend.
+//
+// Same class names, descriptor contents, default parameters, handle flow and error behaviour as the
+// reference's R/include/benchmarks/{ckks,bfv}/*.h; what changes is where the ciphertexts live:
+//   encode / encrypt / decrypt / decode   host (untimed by HEBench), host FHE stand-in
+//   load                                  H2D upload into HBM, sharded / replicated across the GPUs
+//   operate                               batched kernels through include/b200he.h (the timed region)
+//   store                                 D2H gather
+// The CKKS and BFV variants of one workload share a class template (the reference duplicates the file per
+// scheme); namespaces sbe::ckks and sbe::bfv expose them under the reference's names.
+#pragma once
+#include <array>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "hebench/api_bridge/cpp/hebench.hpp"
+
+#include "engine/b200_context.h"
+
+namespace sbe {
+
+// encryption parameters appended to every workload's own parameters
+// (e.g. R/include/benchmarks/ckks/seal_ckks_element_wise_benchmark.h:31-42)
+struct EncryptionParams {
+    std::uint64_t poly_modulus_degree, multiplicative_depth, coeff_modulus_bits, scale_or_plain_bits, num_threads;
+};
+
+// description shared by all workloads: descriptor + defaults + CSV header text
+class B200BenchmarkDescription : public hebench::cpp::BenchmarkDescription
+{
+public:
+    HEBERROR_DECLARE_CLASS_NAME(B200BenchmarkDescription)
+    void destroyBenchmark(hebench::cpp::BaseBenchmark *p_bench) override;
+    std::string getBenchmarkDescription(const hebench::APIBridge::WorkloadParams *p_w_params) const override;
+    // index of the first encryption parameter = number of workload-defined parameters
+    std::size_t extraParamsStart() const { return m_extra_start; }
+    EncryptionParams encryptionParams(const hebench::APIBridge::WorkloadParams &p) const;
+
+protected:
+    void setup(bool ckks, hebench::APIBridge::Workload w, hebench::APIBridge::Category cat, std::int64_t other, const char *algo_name,
+               const char *algo_desc, const std::vector<std::uint64_t> &workload_defaults, const std::vector<const char *> &workload_names,
+               const EncryptionParams &defaults);
+    bool m_ckks              = true;
+    std::size_t m_extra_start = 0;
+    std::string m_algo_name, m_algo_desc;
+};
+
+SEALContextWrapper::Ptr makeContext(bool ckks, const EncryptionParams &ep);
+
+// ------------------------------------------------------------------ element-wise add / multiply, dot product
+enum class VectorOp { Add, Multiply, Dot };
+
+template <bool CKKS> class ElementWiseBenchmarkDescriptionT : public B200BenchmarkDescription
+{
+public:
+    static constexpr const char *AlgorithmName        = "Vector";
+    static constexpr const char *AlgorithmDescription = "One vector per ciphertext";
+    static constexpr std::size_t NumOpParams          = 2;
+    ElementWiseBenchmarkDescriptionT(hebench::APIBridge::Category category, hebench::APIBridge::Workload op);
+    hebench::cpp::BaseBenchmark *createBenchmark(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::WorkloadParams *p_params) override;
+};
+template <bool CKKS> class DotProductBenchmarkDescriptionT : public B200BenchmarkDescription
+{
+public:
+    static constexpr const char *AlgorithmName        = "Vector";
+    static constexpr const char *AlgorithmDescription = "One vector per ciphertext";
+    static constexpr std::size_t NumOpParams          = 2;
+    DotProductBenchmarkDescriptionT(hebench::APIBridge::Category category);
+    hebench::cpp::BaseBenchmark *createBenchmark(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::WorkloadParams *p_params) override;
+};
+
+// operate(): result r = i*b1 + j over the indexer ranges (R/src/benchmarks/ckks/seal_ckks_element_wise_benchmark.cpp:306-366,
+// R/src/benchmarks/ckks/seal_ckks_dot_product_benchmark.cpp:293-347 and the bfv twins)
+template <bool CKKS> class VectorBenchmarkT : public hebench::cpp::BaseBenchmark
+{
+public:
+    HEBERROR_DECLARE_CLASS_NAME(VectorBenchmark)
+    static constexpr std::int64_t tag = 0x1;
+    VectorBenchmarkT(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::BenchmarkDescriptor &bench_desc,
+                     const hebench::APIBridge::WorkloadParams &bench_params, const EncryptionParams &ep, VectorOp op);
+    hebench::APIBridge::Handle encode(const hebench::APIBridge::DataPackCollection *p_parameters) override;
+    void decode(hebench::APIBridge::Handle encoded_data, hebench::APIBridge::DataPackCollection *p_native) override;
+    hebench::APIBridge::Handle encrypt(hebench::APIBridge::Handle encoded_data) override;
+    hebench::APIBridge::Handle decrypt(hebench::APIBridge::Handle encrypted_data) override;
+    hebench::APIBridge::Handle load(const hebench::APIBridge::Handle *p_local_data, std::uint64_t count) override;
+    void store(hebench::APIBridge::Handle remote_data, hebench::APIBridge::Handle *p_local_data, std::uint64_t count) override;
+    hebench::APIBridge::Handle operate(hebench::APIBridge::Handle h_remote_packed, const hebench::APIBridge::ParameterIndexer *p_param_indexers,
+                                       std::uint64_t indexers_count) override;
+    std::int64_t classTag() const override { return BaseBenchmark::classTag() | tag; }
+
+private:
+    SEALContextWrapper::Ptr m_p_ctx_wrapper;
+    hebench::cpp::WorkloadParams::VectorSize m_w_params;
+    VectorOp m_op;
+};
+
+// ------------------------------------------------------------------ matrix multiplication (latency category)
+enum class MatMultAlgo { Val = 0, CipherBatchAxis = 1, Row = 2 };   // descriptor.other, R/src/engine/seal_engine.cpp:135-146
+
+template <bool CKKS> class MatMultBenchmarkDescriptionT : public B200BenchmarkDescription
+{
+public:
+    static constexpr std::size_t NumOpParams = 2;
+    explicit MatMultBenchmarkDescriptionT(MatMultAlgo algo);
+    hebench::cpp::BaseBenchmark *createBenchmark(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::WorkloadParams *p_params) override;
+
+private:
+    MatMultAlgo m_algo;
+};
+
+template <bool CKKS> class MatMultBenchmarkT : public hebench::cpp::BaseBenchmark
+{
+public:
+    HEBERROR_DECLARE_CLASS_NAME(MatMultBenchmark)
+    static constexpr std::int64_t tag = 0x2;
+    MatMultBenchmarkT(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::BenchmarkDescriptor &bench_desc,
+                      const hebench::APIBridge::WorkloadParams &bench_params, const EncryptionParams &ep, MatMultAlgo algo);
+    hebench::APIBridge::Handle encode(const hebench::APIBridge::DataPackCollection *p_parameters) override;
+    void decode(hebench::APIBridge::Handle encoded_data, hebench::APIBridge::DataPackCollection *p_native) override;
+    hebench::APIBridge::Handle encrypt(hebench::APIBridge::Handle encoded_data) override;
+    hebench::APIBridge::Handle decrypt(hebench::APIBridge::Handle encrypted_data) override;
+    hebench::APIBridge::Handle load(const hebench::APIBridge::Handle *p_local_data, std::uint64_t count) override;
+    void store(hebench::APIBridge::Handle remote_data, hebench::APIBridge::Handle *p_local_data, std::uint64_t count) override;
+    hebench::APIBridge::Handle operate(hebench::APIBridge::Handle h_remote_packed, const hebench::APIBridge::ParameterIndexer *p_param_indexers,
+                                       std::uint64_t indexers_count) override;
+    std::int64_t classTag() const override { return BaseBenchmark::classTag() | tag; }
+
+private:
+    typedef typename std::conditional<CKKS, double, std::int64_t>::type Scalar;
+    std::vector<Plaintext> encodeM0(const Scalar *m) const;
+    std::vector<Plaintext> encodeM1(const Scalar *m) const;
+    ShardedCiphertexts operateVal(const std::array<ShardedCiphertexts, 2> &in);
+    ShardedCiphertexts operateRow(const std::array<ShardedCiphertexts, 2> &in);
+    ShardedCiphertexts operateCipherBatchAxis(const std::array<ShardedCiphertexts, 2> &in);
+    SEALContextWrapper::Ptr m_p_ctx_wrapper;
+    hebench::cpp::WorkloadParams::MatrixMultiply m_w_params;
+    MatMultAlgo m_algo;
+};
+
+// ------------------------------------------------------------------ logistic regression, degree-3 sigmoid (CKKS)
+namespace ckks {
+
+class LogRegHornerBenchmarkDescription : public B200BenchmarkDescription
+{
+public:
+    static constexpr const char *AlgorithmName        = "HornerPolyEval";
+    static constexpr const char *AlgorithmDescription = "using Horner method for polynomial evaluation";
+    static constexpr std::uint64_t DefaultBatchSize   = 100;
+    static constexpr std::size_t NumOpParams          = 3;   // W, b, X
+    enum : std::size_t { Index_W = 0, Index_b, Index_X };
+    // (0.5 + 0.15012 x - 0.0015930078125 x^3), R/include/benchmarks/ckks/seal_ckks_logreg_horner.h
+    static constexpr double SigmoidPolyCoeff[] = { 0.5, 0.15012, 0.0, -0.0015930078125 };
+    LogRegHornerBenchmarkDescription(hebench::APIBridge::Category category, std::size_t batch_size = 0);
+    hebench::cpp::BaseBenchmark *createBenchmark(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::WorkloadParams *p_params) override;
+};
+
+class LogRegHornerBenchmark : public hebench::cpp::BaseBenchmark
+{
+public:
+    HEBERROR_DECLARE_CLASS_NAME(ckks::LogRegHornerBenchmark)
+    static constexpr std::int64_t tag                   = 0x4;
+    static constexpr std::int64_t EncodedOpParamsTag    = 0x10;
+    static constexpr std::int64_t EncryptedOpParamsTag  = 0x20;
+    static constexpr std::int64_t EncryptedResultTag    = 0x40;
+    static constexpr std::int64_t EncodedResultTag      = 0x80;
+    LogRegHornerBenchmark(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::BenchmarkDescriptor &bench_desc,
+                          const hebench::APIBridge::WorkloadParams &bench_params, const EncryptionParams &ep);
+    hebench::APIBridge::Handle encode(const hebench::APIBridge::DataPackCollection *p_parameters) override;
+    void decode(hebench::APIBridge::Handle encoded_data, hebench::APIBridge::DataPackCollection *p_native) override;
+    hebench::APIBridge::Handle encrypt(hebench::APIBridge::Handle encoded_data) override;
+    hebench::APIBridge::Handle decrypt(hebench::APIBridge::Handle encrypted_data) override;
+    hebench::APIBridge::Handle load(const hebench::APIBridge::Handle *p_local_data, std::uint64_t count) override;
+    void store(hebench::APIBridge::Handle remote_data, hebench::APIBridge::Handle *p_local_data, std::uint64_t count) override;
+    hebench::APIBridge::Handle operate(hebench::APIBridge::Handle h_remote_packed, const hebench::APIBridge::ParameterIndexer *p_param_indexers,
+                                       std::uint64_t indexers_count) override;
+    std::int64_t classTag() const override { return BaseBenchmark::classTag() | tag; }
+
+private:
+    typedef std::tuple<Plaintext, Plaintext, std::vector<Plaintext>> EncodedOpParams;       // W, b, X
+    typedef std::tuple<Ciphertext, Ciphertext, std::vector<Ciphertext>> EncryptedOpParams;
+    struct LoadedOpParams {                       // W and b replicated, X sharded by sample
+        std::vector<DeviceBatchPtr> W, b;
+        ShardedCiphertexts X;
+    };
+    SEALContextWrapper::Ptr m_p_ctx_wrapper;
+    hebench::cpp::WorkloadParams::LogisticRegression m_w_params;
+    std::vector<Plaintext> m_plain_coeff;
+};
+
+typedef ElementWiseBenchmarkDescriptionT<true> ElementWiseBenchmarkDescription;
+typedef DotProductBenchmarkDescriptionT<true> DotProductBenchmarkDescription;
+typedef VectorBenchmarkT<true> ElementWiseBenchmark;
+typedef VectorBenchmarkT<true> DotProductBenchmark;
+typedef MatMultBenchmarkT<true> MatMultValBenchmark;
+typedef MatMultBenchmarkT<true> MatMultRowLatencyBenchmark;
+typedef MatMultBenchmarkT<true> MatMultCipherBatchAxisBenchmark;
+struct MatMultValBenchmarkDescription : MatMultBenchmarkDescriptionT<true> { MatMultValBenchmarkDescription() : MatMultBenchmarkDescriptionT<true>(MatMultAlgo::Val) {} };
+struct MatMultRowBenchmarkDescription : MatMultBenchmarkDescriptionT<true> { MatMultRowBenchmarkDescription() : MatMultBenchmarkDescriptionT<true>(MatMultAlgo::Row) {} };
+struct MatMultCipherBatchAxisBenchmarkDescription : MatMultBenchmarkDescriptionT<true> { MatMultCipherBatchAxisBenchmarkDescription() : MatMultBenchmarkDescriptionT<true>(MatMultAlgo::CipherBatchAxis) {} };
+}   // namespace ckks
+
+namespace bfv {
+typedef ElementWiseBenchmarkDescriptionT<false> ElementWiseBenchmarkDescription;
+typedef DotProductBenchmarkDescriptionT<false> DotProductBenchmarkDescription;
+typedef VectorBenchmarkT<false> ElementWiseBenchmark;
+typedef VectorBenchmarkT<false> DotProductBenchmark;
+typedef MatMultBenchmarkT<false> MatMultValBenchmark;
+typedef MatMultBenchmarkT<false> MatMultRowLatencyBenchmark;
+typedef MatMultBenchmarkT<false> MatMultCipherBatchAxisBenchmark;
+struct MatMultValBenchmarkDescription : MatMultBenchmarkDescriptionT<false> { MatMultValBenchmarkDescription() : MatMultBenchmarkDescriptionT<false>(MatMultAlgo::Val) {} };
+struct MatMultRowBenchmarkDescription : MatMultBenchmarkDescriptionT<false> { MatMultRowBenchmarkDescription() : MatMultBenchmarkDescriptionT<false>(MatMultAlgo::Row) {} };
+struct MatMultCipherBatchAxisBenchmarkDescription : MatMultBenchmarkDescriptionT<false> { MatMultCipherBatchAxisBenchmarkDescription() : MatMultBenchmarkDescriptionT<false>(MatMultAlgo::CipherBatchAxis) {} };
+}   // namespace bfv
+
+// replicate a host vector of ciphertexts on every GPU
+ShardedCiphertexts replicate(const SEALContextWrapper &ctx, const std::vector<Ciphertext> &src);
+// gather a sharded result vector back to the host (D2H per GPU, concatenated in index order)
+std::vector<Ciphertext> gather(const SEALContextWrapper &ctx, const ShardedCiphertexts &src);
+// decoded values below 5e-5 in magnitude are flushed to 0 so the harness' relative comparison near 0 holds
+// (R/src/benchmarks/ckks/seal_ckks_element_wise_benchmark.cpp:221-226)
+inline double flushTiny(double v) { return (v < 0 ? -v : v) < 0.00005 ? 0.0 : v; }
+
+}   // namespace sbe

@@ -1,0 +1,63 @@
+// b200_types.h -- host/device data types of the B200 HEBench backend.
+// Mirrors the role of R/include/engine/seal_types.h (error code, security id) and replaces the
+// seal::Plaintext / seal::Ciphertext payloads that the reference moves between API calls.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "b200he.h"
+
+#define HEBSEAL_ECODE_SEAL_ERROR 2        // R/include/engine/seal_types.h:13 (any error below the HEBench layer)
+#define HEBENCH_HE_SECURITY_128 0         // R/include/engine/seal_types.h:9
+
+namespace sbe {
+
+// host image of seal::Plaintext: CKKS = NTT form [L][N] with a scale; BFV = coefficients mod t [N]
+struct Plaintext {
+    std::vector<std::uint64_t> data;
+    int L        = 0;      // RNS limbs (CKKS); 0 for BFV
+    double scale = 1.0;
+};
+// host image of seal::Ciphertext: uint64[size][L][N]
+struct Ciphertext {
+    std::vector<std::uint64_t> data;
+    int size     = 0;
+    int L        = 0;
+    bool ntt     = false;
+    double scale = 1.0;
+};
+
+class SEALContextWrapper;
+
+// device-resident std::vector<seal::Ciphertext> on one GPU (RAII over b200he_batch)
+class DeviceBatch
+{
+public:
+    DeviceBatch(b200he_ctx *ctx);
+    ~DeviceBatch();
+    DeviceBatch(const DeviceBatch &) = delete;
+    DeviceBatch &operator=(const DeviceBatch &) = delete;
+    b200he_batch *get() const { return m_b; }
+    b200he_ctx *ctx() const { return m_ctx; }
+    std::uint64_t count() const { return b200he_batch_count(m_b); }
+    int size() const { return b200he_batch_size(m_b); }
+    int level() const { return b200he_batch_level(m_b); }
+    double scale() const { return b200he_batch_scale(m_b); }
+
+private:
+    b200he_ctx *m_ctx;
+    b200he_batch *m_b;
+};
+typedef std::shared_ptr<DeviceBatch> DeviceBatchPtr;
+
+// a vector of ciphertexts sharded over the GPUs of the engine: shard g holds the items
+// [first[g], first[g+1]) of the logical vector (or a full replica when `replicated`)
+struct ShardedCiphertexts {
+    std::vector<DeviceBatchPtr> shard;       // one per GPU (may hold 0 items)
+    std::vector<std::uint64_t> first;        // size n_gpus + 1
+    bool replicated = false;
+    std::uint64_t total() const { return first.empty() ? 0 : first.back(); }
+};
+
+}   // namespace sbe

@@ -1,0 +1,328 @@
+// b200_context.cpp -- SEALContextWrapper of the B200 backend (see b200_context.h).
+// Replaces R/src/engine/seal_context.cpp: key generation / encode / encrypt / decrypt stay on the host,
+// every Evaluator call becomes a call on device batches through include/b200he.h.
+#include "engine/b200_context.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <sstream>
+
+#include "../../hostfhe/hostfhe.h"
+
+namespace sbe {
+
+// ------------------------------------------------------------------ DeviceBatch
+DeviceBatch::DeviceBatch(b200he_ctx *ctx) : m_ctx(ctx), m_b(nullptr)
+{
+    if (b200he_batch_create(ctx, &m_b))
+        throw hebench::cpp::HEBenchError(std::string("DeviceBatch: ") + b200he_last_error(), HEBSEAL_ECODE_SEAL_ERROR);
+}
+DeviceBatch::~DeviceBatch() { b200he_batch_destroy(m_b); }
+
+// ------------------------------------------------------------------ construction
+SEALContextWrapper::Ptr SEALContextWrapper::createCKKSContext(std::size_t poly_modulus_degree, std::size_t num_coeff_moduli,
+                                                              int coeff_moduli_bits, int scale_bits)
+{
+    Ptr p(new SEALContextWrapper());
+    p->init(true, poly_modulus_degree, num_coeff_moduli, coeff_moduli_bits, scale_bits);
+    return p;
+}
+SEALContextWrapper::Ptr SEALContextWrapper::createBFVContext(std::size_t poly_modulus_degree, std::size_t num_coeff_moduli,
+                                                             int coeff_moduli_bits, int plaintext_modulus_bits)
+{
+    Ptr p(new SEALContextWrapper());
+    p->init(false, poly_modulus_degree, num_coeff_moduli, coeff_moduli_bits, plaintext_modulus_bits);
+    return p;
+}
+
+void SEALContextWrapper::check(int rc, const char *what) const
+{
+    if (rc) throw hebench::cpp::HEBenchError(std::string(what) + ": " + b200he_last_error(), HEBSEAL_ECODE_SEAL_ERROR);
+}
+
+void SEALContextWrapper::init(bool ckks, std::size_t N, std::size_t depth, int coeff_bits, int scale_or_plain_bits)
+{
+    if (depth < 1) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Multiplicative depth must be greater than 0."), HEBENCH_ECODE_INVALID_ARGS);
+    if (N < 1024 || N > 32768 || (N & (N - 1)))
+        throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Polynomial modulus degree must be a power of 2 in [1024, 32768]."), HEBENCH_ECODE_INVALID_ARGS);
+    m_ckks       = ckks;
+    m_N          = N;
+    m_K          = depth + 1;
+    m_scale_bits = scale_or_plain_bits;
+    std::uint64_t seed = 0x9e3779b97f4a7c15ull;
+    if (const char *e = getenv("HEB_B200_SEED")) seed = strtoull(e, nullptr, 0);
+    m_host = hfhe_create(ckks ? HFHE_CKKS : HFHE_BFV, N, depth, coeff_bits, scale_or_plain_bits, seed);
+    if (!m_host) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Invalid encryption parameters."), HEBSEAL_ECODE_SEAL_ERROR);
+    m_scale = ckks ? hfhe_scale(m_host) : 1.0;
+    m_t     = ckks ? 0 : hfhe_plain_modulus(m_host);
+
+    // one device context per GPU; keys replicated
+    int n_gpus = 1;
+    if (const char *e = getenv("HEB_B200_GPUS")) n_gpus = std::max(1, atoi(e));
+    const std::uint64_t *keyr = hfhe_relin_key(m_host);
+    const std::size_t n_gal   = hfhe_galois_count(m_host);
+    for (int g = 0; g < n_gpus; ++g) {
+        b200he_ctx *c = nullptr;
+        check(b200he_ctx_create(ckks ? B200HE_CKKS : B200HE_BFV, (uint32_t)N, (uint32_t)m_K, hfhe_moduli(m_host), hfhe_psi(m_host), m_t, g, &c),
+              "b200he_ctx_create");
+        m_dev.push_back(c);
+        check(b200he_set_relin_key(c, keyr), "b200he_set_relin_key");
+        for (std::size_t i = 0; i < n_gal; ++i) {
+            const uint32_t elt = hfhe_galois_elt(m_host, i);
+            check(b200he_set_galois_key(c, elt, hfhe_galois_key(m_host, elt)), "b200he_set_galois_key");
+        }
+    }
+}
+
+SEALContextWrapper::~SEALContextWrapper()
+{
+    m_mask_cache.clear();
+    for (b200he_ctx *c : m_dev) b200he_ctx_destroy(c);
+    if (m_host) hfhe_destroy(m_host);
+}
+
+std::vector<int> SEALContextWrapper::coeffModulusBits() const
+{
+    std::vector<int> bits;
+    const std::uint64_t *q = hfhe_moduli(m_host);
+    for (std::size_t i = 0; i < m_K; ++i) {
+        int b = 0;
+        for (std::uint64_t v = q[i]; v; v >>= 1) ++b;
+        bits.push_back(b);
+    }
+    return bits;
+}
+
+// ------------------------------------------------------------------ host side
+Plaintext SEALContextWrapper::encodeVector(const std::vector<double> &values) { return encodeVector(values, m_scale); }
+Plaintext SEALContextWrapper::encodeVector(const std::vector<double> &values, double scale)
+{
+    if (values.size() > slotCount())
+        throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Not enough slots available to create packed plaintext"), HEBENCH_ECODE_INVALID_ARGS);
+    Plaintext p;
+    p.L     = (int)topLevel();
+    p.scale = scale;
+    p.data.resize(topLevel() * m_N);
+    hfhe_ckks_encode(m_host, values.data(), values.size(), scale, p.data.data());
+    return p;
+}
+Plaintext SEALContextWrapper::encodeVector(const std::vector<std::int64_t> &values)
+{
+    if (values.size() > slotCount())
+        throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Not enough slots available to create packed plaintext"), HEBENCH_ECODE_INVALID_ARGS);
+    Plaintext p;
+    p.data.resize(m_N);
+    hfhe_bfv_encode(m_host, values.data(), values.size(), p.data.data());
+    return p;
+}
+std::vector<double> SEALContextWrapper::decodeCKKS(const Plaintext &plain)
+{
+    std::vector<double> out(m_N / 2);
+    hfhe_ckks_decode(m_host, plain.data.data(), (std::size_t)plain.L, plain.scale, out.data());
+    return out;
+}
+std::vector<std::int64_t> SEALContextWrapper::decodeBFV(const Plaintext &plain)
+{
+    std::vector<std::int64_t> out(m_N);
+    hfhe_bfv_decode(m_host, plain.data.data(), out.data());
+    return out;
+}
+Ciphertext SEALContextWrapper::encrypt(const Plaintext &plain)
+{
+    Ciphertext c;
+    c.size  = 2;
+    c.L     = (int)topLevel();
+    c.ntt   = m_ckks;
+    c.scale = m_ckks ? plain.scale : 1.0;
+    c.data.resize(2 * topLevel() * m_N);
+    std::lock_guard<std::mutex> lock(m_host_mtx);
+    hfhe_encrypt(m_host, plain.data.data(), c.data.data());
+    return c;
+}
+std::vector<Ciphertext> SEALContextWrapper::encrypt(const std::vector<Plaintext> &plain)
+{
+    std::vector<Ciphertext> out;
+    out.reserve(plain.size());
+    for (const Plaintext &p : plain) out.push_back(encrypt(p));
+    return out;
+}
+Plaintext SEALContextWrapper::decrypt(const Ciphertext &cipher)
+{
+    Plaintext p;
+    p.L     = m_ckks ? cipher.L : 0;
+    p.scale = cipher.scale;
+    p.data.resize(m_ckks ? (std::size_t)cipher.L * m_N : m_N);
+    hfhe_decrypt(m_host, cipher.data.data(), (std::size_t)cipher.size, (std::size_t)cipher.L, p.data.data());
+    return p;
+}
+std::vector<Plaintext> SEALContextWrapper::decrypt(const std::vector<Ciphertext> &cipher)
+{
+    std::vector<Plaintext> out;
+    out.reserve(cipher.size());
+    for (const Ciphertext &c : cipher) out.push_back(decrypt(c));
+    return out;
+}
+
+// ------------------------------------------------------------------ device side
+std::vector<std::uint64_t> SEALContextWrapper::partition(std::uint64_t n) const
+{
+    const std::uint64_t g = m_dev.size();
+    std::vector<std::uint64_t> first(g + 1, 0);
+    for (std::uint64_t i = 0; i < g; ++i) first[i + 1] = first[i] + n / g + (i < n % g ? 1 : 0);
+    return first;
+}
+
+DeviceBatchPtr SEALContextWrapper::upload(int g, const std::vector<Ciphertext> &src, std::size_t first, std::size_t n) const
+{
+    DeviceBatchPtr b = newBatch(g);
+    if (first + n > src.size()) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("upload range out of bounds"), HEBENCH_ECODE_INVALID_ARGS);
+    if (n == 0) {
+        check(b200he_batch_resize(b->get(), 0, 2, (int)topLevel(), m_ckks, m_scale), "b200he_batch_resize");
+        return b;
+    }
+    const Ciphertext &c0 = src[first];
+    check(b200he_batch_resize(b->get(), n, c0.size, c0.L, c0.ntt, c0.scale), "b200he_batch_resize");
+    for (std::size_t i = 0; i < n; ++i) {
+        const Ciphertext &c = src[first + i];
+        if (c.size != c0.size || c.L != c0.L || c.ntt != c0.ntt)
+            throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("ciphertexts of one batch must share size, level and form"), HEBENCH_ECODE_INVALID_ARGS);
+        check(b200he_batch_upload(b->get(), i, 1, c.data.data()), "b200he_batch_upload");
+    }
+    check(b200he_ctx_sync(m_dev[g]), "b200he_ctx_sync");   // host vectors may go away
+    return b;
+}
+DeviceBatchPtr SEALContextWrapper::upload(int g, const Ciphertext &src) const
+{
+    std::vector<Ciphertext> v(1, src);
+    return upload(g, v, 0, 1);
+}
+DeviceBatchPtr SEALContextWrapper::uploadPlain(int g, const std::vector<Plaintext> &src) const
+{
+    DeviceBatchPtr b = newBatch(g);
+    if (src.empty()) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("empty plaintext batch"), HEBENCH_ECODE_INVALID_ARGS);
+    check(b200he_batch_resize(b->get(), src.size(), 1, src[0].L, 1, src[0].scale), "b200he_batch_resize");
+    for (std::size_t i = 0; i < src.size(); ++i) check(b200he_batch_upload(b->get(), i, 1, src[i].data.data()), "b200he_batch_upload");
+    check(b200he_ctx_sync(m_dev[g]), "b200he_ctx_sync");
+    return b;
+}
+std::vector<Ciphertext> SEALContextWrapper::download(const DeviceBatch &b) const
+{
+    std::vector<Ciphertext> out(b.count());
+    const std::size_t words = (std::size_t)b.size() * b.level() * m_N;
+    for (std::size_t i = 0; i < out.size(); ++i) {
+        Ciphertext &c = out[i];
+        c.size        = b.size();
+        c.L           = b.level();
+        c.ntt         = b200he_batch_ntt_form(b.get()) != 0;
+        c.scale       = b.scale();
+        c.data.resize(words);
+        check(b200he_batch_download(b.get(), i, 1, c.data.data()), "b200he_batch_download");
+    }
+    return out;
+}
+void SEALContextWrapper::syncAll() const
+{
+    for (b200he_ctx *c : m_dev) check(b200he_ctx_sync(c), "b200he_ctx_sync");
+}
+
+// R/src/engine/seal_context.cpp:255-263: the ciphertext with more limbs is switched down (CKKS: limbs dropped)
+void SEALContextWrapper::matchLevel(DeviceBatch &a, DeviceBatch &b) const
+{
+    if (a.level() > b.level()) check(b200he_mod_drop(a.ctx(), a.get(), b.level(), a.get()), "b200he_mod_drop");
+    else if (a.level() < b.level()) check(b200he_mod_drop(b.ctx(), b.get(), a.level(), b.get()), "b200he_mod_drop");
+}
+// R/src/engine/seal_context.cpp:289-347.  count == 0 (fresh encryption of zero in the reference) is rejected.
+void SEALContextWrapper::accumulateBFV(DeviceBatch &cipher, std::size_t count) const
+{
+    check(b200he_accumulate(cipher.ctx(), cipher.get(), count), "b200he_accumulate");
+}
+void SEALContextWrapper::accumulateCKKS(DeviceBatch &cipher, std::size_t count) const
+{
+    if (count > slotCount()) count = slotCount();
+    check(b200he_accumulate(cipher.ctx(), cipher.get(), count), "b200he_accumulate");
+}
+
+// masks e_i = encode(unit vector i of length `total`, scale()) switched down to `level`
+// (R/src/engine/seal_context.cpp:382-388); deterministic, so they are cached in HBM per shape.
+DeviceBatchPtr SEALContextWrapper::maskBatch(int g, std::size_t first_index, std::size_t n, std::size_t total, int level)
+{
+    std::ostringstream key;
+    key << g << ':' << first_index << ':' << n << ':' << total << ':' << level;
+    auto it = m_mask_cache.find(key.str());
+    if (it != m_mask_cache.end()) return it->second;
+    std::vector<Plaintext> masks(n);
+#pragma omp parallel for
+    for (long i = 0; i < (long)n; ++i) {
+        std::vector<double> identity(total, 0.0);
+        identity[first_index + i] = 1.0;
+        Plaintext p = encodeVector(identity, m_scale);
+        p.data.resize((std::size_t)level * m_N);   // mod_switch_to_inplace(plain): drop the trailing limbs
+        p.L = level;
+        masks[i] = std::move(p);
+    }
+    DeviceBatchPtr b = uploadPlain(g, masks);
+    m_mask_cache[key.str()] = b;
+    return b;
+}
+
+// R/src/engine/seal_context.cpp:349-415 on one GPU's shard of the samples
+DeviceBatchPtr SEALContextWrapper::collapseCKKS(DeviceBatch &ciphers, std::size_t first_index, std::size_t total, bool add_encrypted_zero)
+{
+    b200he_ctx *c = ciphers.ctx();
+    int g = 0;
+    for (std::size_t i = 0; i < m_dev.size(); ++i)
+        if (m_dev[i] == c) g = (int)i;
+    const std::size_t n = ciphers.count();
+    DeviceBatchPtr result = newBatch(g);
+    if (n > 0) {
+        std::vector<int32_t> steps(n);
+        for (std::size_t i = 0; i < n; ++i) steps[i] = -(int32_t)(first_index + i);
+        check(b200he_rotate_each(c, ciphers.get(), steps.data(), ciphers.get()), "b200he_rotate_each");
+        DeviceBatchPtr masks = maskBatch(g, first_index, n, total, ciphers.level());
+        check(b200he_multiply_plain(c, ciphers.get(), masks->get(), nullptr, ciphers.get()), "b200he_multiply_plain");
+        check(b200he_relinearize(c, ciphers.get(), ciphers.get()), "b200he_relinearize");   // size 2: no-op, as in the reference
+        check(b200he_rescale_to_next(c, ciphers.get(), ciphers.get()), "b200he_rescale_to_next");
+        check(b200he_batch_set_scale(ciphers.get(), m_scale), "b200he_batch_set_scale");
+        check(b200he_sum(c, ciphers.get(), result->get()), "b200he_sum");
+    }
+    if (add_encrypted_zero) {
+        // retval = Enc(0) at the top level, switched down to the summands' level, scale forced (:360-361, :397-400)
+        Plaintext zero = encodeVector(std::vector<double>(1, 0.0), m_scale);
+        DeviceBatchPtr z = upload(g, encrypt(zero));
+        if (n > 0) {
+            check(b200he_mod_drop(c, z->get(), result->level(), z->get()), "b200he_mod_drop");
+            check(b200he_batch_set_scale(z->get(), result->scale()), "b200he_batch_set_scale");
+            check(b200he_add(c, z->get(), nullptr, result->get(), nullptr, 1, result->get()), "b200he_add");
+        } else
+            result = z;
+    }
+    return result;
+}
+
+// R/src/engine/seal_context.cpp:417-458 (Horner), cipher_input and the result are single-ciphertext batches
+DeviceBatchPtr SEALContextWrapper::evaluatePolynomial(DeviceBatch &cipher_input, const std::vector<Plaintext> &plain_coefficients)
+{
+    if (plain_coefficients.empty())
+        throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Polynomial must have, at least, 1 coefficient."), HEBENCH_ECODE_INVALID_ARGS);
+    b200he_ctx *c = cipher_input.ctx();
+    int g = 0;
+    for (std::size_t i = 0; i < m_dev.size(); ++i)
+        if (m_dev[i] == c) g = (int)i;
+    auto it = plain_coefficients.rbegin();
+    DeviceBatchPtr retval = upload(g, encrypt(*it));
+    for (++it; it != plain_coefficients.rend(); ++it) {
+        matchLevel(cipher_input, *retval);
+        check(b200he_multiply(c, retval->get(), nullptr, cipher_input.get(), nullptr, 1, retval->get()), "b200he_multiply");
+        check(b200he_relinearize(c, retval->get(), retval->get()), "b200he_relinearize");
+        check(b200he_rescale_to_next(c, retval->get(), retval->get()), "b200he_rescale_to_next");
+        Plaintext p = *it;   // mod_switch_to_inplace(plain, retval.parms_id())
+        p.data.resize((std::size_t)retval->level() * m_N);
+        p.L = retval->level();
+        DeviceBatchPtr dp = uploadPlain(g, std::vector<Plaintext>(1, p));
+        check(b200he_batch_set_scale(retval->get(), p.scale), "b200he_batch_set_scale");
+        check(b200he_add_plain(c, retval->get(), dp->get(), nullptr, retval->get()), "b200he_add_plain");
+    }
+    return retval;
+}
+
+}   // namespace sbe

@@ -510,6 +510,14 @@ extern "C" int b200he_batch_download(const b200he_batch *b, uint64_t first, uint
     CK(cudaGetLastError());
     return 0;
 }
+extern "C" int b200he_batch_download_async(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host)
+{
+    if (!b || !host) return fail("batch_download_async: NULL argument");
+    if (first + n > b->count) return fail("batch_download_async: range exceeds count");
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaMemcpyAsync(host, b->d + first * b->ct_words(), n * b->ct_words() * 8, cudaMemcpyDeviceToHost, b->ctx->stream));
+    return 0;
+}
 extern "C" uint64_t b200he_batch_count(const b200he_batch *b) { return b ? b->count : 0; }
 extern "C" int b200he_batch_size(const b200he_batch *b) { return b ? b->size : 0; }
 extern "C" int b200he_batch_level(const b200he_batch *b) { return b ? b->L : 0; }
@@ -938,6 +946,94 @@ static int rotate_rec(b200he_ctx *c, const b200he_batch *in, int step, b200he_ba
         cur = out;
     }
     if (cur == in && out != in) return b200he_gather(c, in, nullptr, in->count, out);
+    return 0;
+}
+
+// rotate ciphertext i by steps[i] (the collapse step of logistic regression rotates sample i by -i,
+// R/src/engine/seal_context.cpp:378).  Every ciphertext goes through exactly the key switches SEAL's
+// rotate_vector would apply to it -- the non-adjacent form of its own step, least significant term first --
+// but ciphertexts that share a term are switched together: for each power of two and sign, gather the
+// ciphertexts whose decomposition holds that term, apply the Galois element once, scatter back.
+extern "C" int b200he_rotate_each(b200he_ctx *c, const b200he_batch *in, const int32_t *steps, b200he_batch *out)
+{
+    if (!c || !in || !out || !steps) return fail("rotate_each: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("rotate_each: batch belongs to another context");
+    if (in->size != 2) return fail("rotate_each: ciphertext size must be 2");
+    CK(cudaSetDevice(c->device));
+    const uint64_t n = in->count;
+    const int half = (int)(c->N / 2);
+    // term lists: terms[k][sign] = ciphertexts whose step has +-2^k in its decomposition
+    std::vector<std::vector<u32>> plus(32), minus(32);
+    for (uint64_t i = 0; i < n; i++) {
+        const int step = steps[i];
+        if (step == 0) continue;
+        if (step <= -half || step >= half) return fail("rotate_each: step %d of ciphertext %llu out of range", step, (unsigned long long)i);
+        const u32 elt = elt_from_step(c, step);
+        if (c->gal.count(elt)) {   // a key for the whole step: single switch, like SEAL
+            int k = 0;
+            const int a = step < 0 ? -step : step;
+            if ((a & (a - 1)) == 0) {
+                while ((1 << k) < a) k++;
+                (step < 0 ? minus : plus)[k].push_back((u32)i);
+                continue;
+            }
+            return fail("rotate_each: steps with a dedicated non-power-of-two key are not supported");
+        }
+        int v = step < 0 ? -step : step, nterms = 0;
+        for (int k = 0; v; k++) {
+            const int z = (v & 1) ? 2 - (v & 3) : 0;
+            v = (v - z) >> 1;
+            if (!z) continue;
+            nterms++;
+            if ((1 << k) == half) continue;
+            const bool neg = (step < 0) != (z < 0);
+            (neg ? minus : plus)[k].push_back((u32)i);
+        }
+        if (nterms == 1) return fail("rotate_each: Galois key for step %d missing", step);
+    }
+    if (out != in) TRY(b200he_gather(c, in, nullptr, n, out));
+    b200he_batch *sub = nullptr, *rot = nullptr;
+    TRY(b200he_batch_create(c, &sub));
+    TRY(b200he_batch_create(c, &rot));
+    int rc = 0;
+    for (int k = 0; k < 32 && !rc; k++)
+        for (int sgn = 0; sgn < 2 && !rc; sgn++) {
+            const std::vector<u32> &ids = sgn ? minus[k] : plus[k];
+            if (ids.empty()) continue;
+            const int step = sgn ? -(1 << k) : (1 << k);
+            const u32 elt = elt_from_step(c, step);
+            if (!c->gal.count(elt)) { rc = fail("rotate_each: Galois key for step %d missing", step); break; }
+            rc = b200he_gather(c, out, ids.data(), ids.size(), sub);
+            if (!rc) rc = b200he_apply_galois(c, sub, elt, rot);
+            if (!rc) {
+                DevIdx di(c);
+                rc = di.set(ids.data(), ids.size(), n, "rotate_each");
+                if (!rc) {
+                    CopyArgs C{};
+                    C.src = rot->d; C.dst = out->d; C.idx = nullptr; C.dst_idx = di.d;
+                    C.src_stride = rot->ct_words(); C.dst_stride = out->ct_words(); C.polys = 2; C.L_in = in->L; C.L_out = in->L; C.n = ids.size();
+                    LAUNCH(c, B200HE_KERN_COPY, k_copy_limbs, blocks_for(ids.size() * out->ct_words() / 2), 256, 0, c->T, C);
+                    if (cudaGetLastError() != cudaSuccess) rc = fail("rotate_each: scatter launch failed");
+                }
+            }
+        }
+    b200he_batch_destroy(sub);
+    b200he_batch_destroy(rot);
+    return rc;
+}
+
+// out (1 ciphertext) = sum of all ciphertexts of in
+extern "C" int b200he_sum(b200he_ctx *c, const b200he_batch *in, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("sum: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("sum: batch belongs to another context");
+    if (in->count == 0) return fail("sum: empty batch");
+    CK(cudaSetDevice(c->device));
+    OutBuf ob(out, in);
+    TRY(ob.shape(1, in->size, in->L, in->ntt, in->scale));
+    LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_batch_sum, blocks_for(in->ct_words() / 2), 256, 0, c->T, in->d, ob.ptr(), (size_t)in->count, in->size, in->L);
+    LAUNCH_CHECK();
+    ob.commit();
     return 0;
 }
 

@@ -540,7 +540,8 @@ __global__ void __launch_bounds__(256) k_galois_coeff(Tables T, GaloisArgs A)
 struct CopyArgs {
     const u64 *src;
     u64 *dst;
-    const u32 *idx;
+    const u32 *idx;       // gather map (source ciphertext of output i), nullable
+    const u32 *dst_idx;   // scatter map (destination ciphertext of item i), nullable
     size_t src_stride, dst_stride;
     int polys, L_in, L_out;
     size_t n;
@@ -552,9 +553,27 @@ __global__ void __launch_bounds__(256) k_copy_limbs(Tables T, CopyArgs A)
     if (gid >= A.n * per_ct) return;
     const size_t i = gid / per_ct, rem = (gid % per_ct) * 2;
     const size_t limb_idx = rem / N, e = rem % N, p = limb_idx / A.L_out, l = limb_idx % A.L_out;
-    const size_t is = A.idx ? A.idx[i] : i;
+    const size_t is = A.idx ? A.idx[i] : i, id = A.dst_idx ? A.dst_idx[i] : i;
     ulonglong2 v = ld2(A.src + is * A.src_stride + (p * A.L_in + l) * N + e);
-    st2(A.dst + i * A.dst_stride + rem, v.x, v.y);
+    st2(A.dst + id * A.dst_stride + rem, v.x, v.y);
+}
+
+// out[0] = sum_i in[i] over a batch (collapse of per-sample ciphertexts, R/src/engine/seal_context.cpp:397-400):
+// one thread per coefficient pair walks the batch; modular adds commute, so any order gives the reference's bits.
+__global__ void __launch_bounds__(256) k_batch_sum(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst, size_t n, int polys, int L)
+{
+    const size_t N = T.N, per_ct = (size_t)polys * L * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_ct) return;
+    const size_t rem = gid * 2;
+    const u64 q = T.mods[(rem / N) % L].q;
+    u64 s0 = 0, s1 = 0;
+    for (size_t i = 0; i < n; i++) {
+        const ulonglong2 v = ld2(src + i * 2 * per_ct + rem);
+        s0 = add_mod(s0, v.x, q);
+        s1 = add_mod(s1, v.y, q);
+    }
+    st2(dst + rem, s0, s1);
 }
 
 }   // namespace b200he

@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200he_batch_resize": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double]),
     "b200he_batch_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_batch_download": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b200he_batch_download_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_batch_count": (C.c_uint64, [C.c_void_p]),
     "b200he_batch_size": (C.c_int, [C.c_void_p]),
     "b200he_batch_level": (C.c_int, [C.c_void_p]),
@@ -49,6 +50,8 @@ SIGNATURES = {
     "b200he_relinearize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200he_rotate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200he_rotate_columns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200he_rotate_each": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "b200he_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200he_apply_galois": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200he_rescale_to_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200he_mod_drop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -149,8 +152,9 @@ class Batch:
         """raw pointer upload (pinned host memory), asynchronous"""
         self.ctx._ck(self.lib.b200he_batch_upload(self.h, first, n, ptr))
 
-    def download_to(self, ptr, first, n):
-        self.ctx._ck(self.lib.b200he_batch_download(self.h, first, n, ptr))
+    def download_to(self, ptr, first, n, wait=True):
+        fn = self.lib.b200he_batch_download if wait else self.lib.b200he_batch_download_async
+        self.ctx._ck(fn(self.h, first, n, ptr))
 
     def download(self, first=0, n=None):
         n = self.count - first if n is None else n
@@ -260,6 +264,16 @@ class Context:
 
     def rotate(self, a, step, out=None):
         return self._unary(self.lib.b200he_rotate, a, out, int(step))
+
+    def rotate_each(self, a, steps, out=None):
+        out = out or Batch(self)
+        st = np.ascontiguousarray(steps, dtype=np.int32)
+        assert len(st) == a.count
+        self._ck(self.lib.b200he_rotate_each(self.h, a.h, st.ctypes.data_as(C.POINTER(C.c_int32)), out.h))
+        return out
+
+    def sum(self, a, out=None):
+        return self._unary(self.lib.b200he_sum, a, out)
 
     def rotate_columns(self, a, out=None):
         return self._unary(self.lib.b200he_rotate_columns, a, out)

@@ -24,7 +24,7 @@ def chain(N, bits):
 class Env:
     """a device context + the oracle context on the same chain, with random keys"""
 
-    def __init__(self, lib, scheme, N, bits, seed=1234, plain_bits=20, galois_steps=(1, 2, 4, 8, -1, -4), columns=False):
+    def __init__(self, lib, scheme, N, bits, seed=1234, plain_bits=20, galois_steps=(1, 2, 4, 8, -1, -2, -4, -8), columns=False):
         self.scheme, self.N = scheme, N
         self.moduli = chain(N, bits)
         self.K = len(bits)
@@ -294,3 +294,20 @@ def case_decrypt_level(lib, N, n=100):
     want = float(np.dot(u, v))
     assert abs(dec[0] - want) < 1e-4 * max(1.0, abs(want)), (dec[0], want)
     ctx.close()
+
+
+def case_rotate_each_and_sum(env, n=7, L=None):
+    """collapse building blocks: per-ciphertext rotation steps (sample i rotated by -i) and the batch sum"""
+    L = env.Ltop if L is None else L
+    x = env.rand_ct(n, L=L)
+    X = env.batch(x, L=L)
+    steps = [-i for i in range(n)]
+    got = env.ctx.rotate_each(X, steps).download()
+    for i in range(n):
+        want = x[i].reshape(-1) if i == 0 else env.orc.rotate(L, x[i].reshape(-1), -i, env.gkeys)
+        eq(got[i], want, f"rotate_each ct{i} by {-i}")
+    s = env.ctx.sum(X).download()
+    want = x[0].reshape(-1).copy()
+    for i in range(1, n):
+        want = env.orc.add(L, 2, want, x[i].reshape(-1))
+    eq(s[0], want, "batch sum")

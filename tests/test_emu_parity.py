@@ -51,6 +51,10 @@ def test_rescale(ckks):
     parity.case_rescale(ckks)
 
 
+def test_rotate_each_and_sum(ckks):
+    parity.case_rotate_each_and_sum(ckks)
+
+
 def test_plain(ckks):
     parity.case_plain(ckks)
 
