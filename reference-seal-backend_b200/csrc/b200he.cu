@@ -392,7 +392,7 @@ extern "C" int b200he_ctx_set_workspace(b200he_ctx *c, uint64_t bytes)
 // ------------------------------------------------------------------------------------ keys
 static size_t key_words(const b200he_ctx *c) { return (size_t)(c->K - 1) * 2 * c->K * c->N; }
 
-// device layout of a key: [key words | Shoup quotients of the key words]
+// device layout of a key: 2 * key_words, residues interleaved with their Shoup quotients (kernels.cuh key_word_index)
 static int upload_key(b200he_ctx *c, u64 *d, const uint64_t *key)
 {
     const size_t words = key_words(c);
@@ -403,10 +403,16 @@ static int upload_key(b200he_ctx *c, u64 *d, const uint64_t *key)
                 for (size_t n = 0; n < c->N; n++)
                     if (p[n] >= q) return fail("set key: residue out of range (digit %zu, component %zu, limb %zu)", J, k, l);
             }
-    CK(cudaMemcpyAsync(d, key, words * 8, cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, B200HE_KERN_COPY, k_shoup_quotients, blocks_for(words), 256, 0, c->T, d, d + words, (int)c->K, words);
-    LAUNCH_CHECK();
-    CK(cudaStreamSynchronize(c->stream));
+    u64 *stage = (u64 *)c->pool.get(words * 8);
+    if (!stage) return fail("set key: out of device memory");
+    cudaError_t e = cudaMemcpyAsync(stage, key, words * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        LAUNCH(c, B200HE_KERN_COPY, k_shoup_quotients, blocks_for(words), 256, 0, c->T, stage, d, (int)c->K, words, c->lognl);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    c->pool.put(stage);
+    if (e != cudaSuccess) return fail("set key: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -823,7 +829,7 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
         } else {
             A.tcoef = tg; A.tcoef_stride = t_stride; A.target = nullptr; A.target_stride = 0;
         }
-        A.key = key; A.key_s = key + key_words(c); A.acc = acc; A.rp = rp; A.L = L; A.K = (int)K; A.B = (int)nb;
+        A.key = key; A.acc = acc; A.rp = rp; A.L = L; A.K = (int)K; A.B = (int)nb;
         NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_KS_INNER, k_ks_inner<LG>, (unsigned)((nb * (L + 1)) << c->c), NttCfg<LG>::THREADS,
                                KsCfg<LG>::SMEM_BYTES, c->T, A, c->c));
         if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: k_ks_inner launch failed"); break; }

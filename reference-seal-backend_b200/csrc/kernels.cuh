@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd(Tables T, con
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     canon_all(x, m);
-    for_pairs_contig(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
+    contig_to_co(x, sm, tid);
+    for_pairs_co(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
 }
 
 // ------------------------------------------------------------------------------------ K2
@@ -151,11 +152,12 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     u64 x[16];
     TwRegs<LOGN, Sched<LOGN>::NP - 1> tl;
     load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, (1 << c) + r);
-    for_pairs_contig(tid, [&](int reg, int e) {
+    for_pairs_co(tid, [&](int reg, int e) {
         ulonglong2 v = ldg2(in + e);
         x[reg] = v.x;
         x[reg + 1] = v.y;
     });
+    co_to_contig(x, sm, tid);
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     if (c == 0) {
         ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0, tl);
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict_
 //
 // One CTA owns (ciphertext b, output modulus I[, chunk r]) and loops over the L digits: the digit is
 // lifted and transformed in registers, then multiplied into both key components.  The keys carry
-// their Shoup quotients (key_s, computed once at upload by k_shoup_quotients), so a multiply-
+// their Shoup quotients (interleaved at upload by k_shoup_quotients), so a multiply-
 // accumulate is one shoup_mad -- 10 integer multiply-adds, valid for ANY 64-bit digit value (the
 // transform output needs no reduction) -- and the accumulators stay lazy (Mod::acc_period).  The two
 // accumulator limbs live in shared memory between digits ([p][tid] pairs, conflict-free 128-bit
@@ -224,8 +226,7 @@ struct KsInnerArgs {
     size_t tcoef_stride;
     const u64 *target;     // NTT-form target (CKKS) or nullptr (BFV): target + b*target_stride + J*N
     size_t target_stride;
-    const u64 *key;        // [Ltop][2][K][N]
-    const u64 *key_s;      // Shoup quotients of key, same layout
+    const u64 *key;        // [Ltop][2][K] limbs of 2N words: keys interleaved with their Shoup quotients (k_shoup_quotients)
     u64 *acc;              // [B][2][L+1][N]
     u64 *rp;               // [B][2][N]: rounded special-prime limb in coefficient form (written when c == 0)
     int L, K, B;           // B = ciphertexts in this launch
@@ -258,11 +259,12 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
         u64 x[16];
         if (A.target && I == J) {
             const u64 *tp = A.target + (size_t)b * A.target_stride + (size_t)J * N + off;
-            for_pairs_contig(tid, [&](int reg, int e) {
+            for_pairs_co(tid, [&](int reg, int e) {
                 ulonglong2 v = ldg2(tp + e);
                 x[reg] = v.x;
                 x[reg + 1] = v.y;
             });
+            co_to_contig(x, sm, tid);
         } else {
             const u64 *tp = A.tcoef + (size_t)b * A.tcoef_stride + (size_t)J * N;
             TwRegs<LOGN, 0> t0;
@@ -276,13 +278,14 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
         const bool fold = ((J + 1) % (int)m.acc_period) == 0;
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const size_t koff = (((size_t)J * 2 + k) * A.K + ki) * N + off + 16 * tid;
-            const u64 *kp = A.key + koff, *ksp = A.key_s + koff;
+            // device key layout (key_limb_index): per limb and chunk [p][tid][k(e), k(e+1), k'(e), k'(e+1)], e = 16 tid + 2p,
+            // k' = Shoup quotient: a warp's loads cover 1 KiB of contiguous memory per p
+            const u64 *kp = A.key + 2 * ((((size_t)J * 2 + k) * A.K + ki) * N + off) + 4 * tid;
             ulonglong2 kv[8], ks[8], a[8];
 #pragma unroll
             for (int p = 0; p < 8; p++) {   // all 16 key loads in flight before the first use
-                kv[p] = ldg2(kp + 2 * p);
-                ks[p] = ldg2(ksp + 2 * p);
+                kv[p] = ldg2(kp + (size_t)p * 4 * TH);
+                ks[p] = ldg2(kp + (size_t)p * 4 * TH + 2);
             }
 #pragma unroll
             for (int p = 0; p < 8; p++) a[p] = ld2(acc_sm[k] + (p * TH + tid) * 2);
@@ -322,24 +325,40 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
         }
         return;
     }
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 2; k++) {
         u64 *o = A.acc + (((size_t)b * 2 + k) * (L + 1) + I) * N + off;
-        for_pairs_contig(tid, [&](int reg, int e) {
+        u64 x[16];
+        for_pairs_contig(tid, [&](int reg, int) {
             const ulonglong2 a = ld2(acc_sm[k] + ((reg >> 1) * TH + tid) * 2);
-            st2(o + e, reduce_full(a.x, m), reduce_full(a.y, m));
+            x[reg] = reduce_full(a.x, m);
+            x[reg + 1] = reduce_full(a.y, m);
         });
+        contig_to_co(x, sm, tid);
+        for_pairs_co(tid, [&](int reg, int e) { st2(o + e, x[reg], x[reg + 1]); });
+        warp_sync();   // the slice is rewritten by the next component
     }
 }
 
-// Shoup quotients floor(k * 2^64 / q) of a key-switching key [Ltop][2][K][N], once per upload
+// Device form of a key-switching key, built once per upload from SEAL's [Ltop][2][K][N] array: every limb becomes
+// 2N words holding the key residues interleaved with their Shoup quotients floor(k * 2^64 / q) in the order
+// k_ks_inner consumes them -- chunk r of NL = 16*TH coefficients, then [p][tid][k(e), k(e+1), k'(e), k'(e+1)] with
+// e = 16 tid + 2p -- so the inner product reads the key with fully coalesced 128-bit loads.
 // (restoring division, 64 steps: k < q < 2^61 so the running remainder never overflows).
-__global__ void __launch_bounds__(256) k_shoup_quotients(Tables T, const u64 *__restrict__ key, u64 *__restrict__ key_s, int K, size_t words)
+__host__ __device__ __forceinline__ size_t key_word_index(size_t limb, size_t e, size_t N, int lognl)
+{
+    const size_t NL = (size_t)1 << lognl, TH = NL / 16;
+    const size_t r = e >> lognl, el = e & (NL - 1), tid = el >> 4, p = (el & 15) >> 1, h = el & 1;
+    return 2 * (limb * N + r * NL) + (p * TH + tid) * 4 + h;
+}
+__global__ void __launch_bounds__(256) k_shoup_quotients(Tables T, const u64 *__restrict__ key, u64 *__restrict__ dkey, int K, size_t words, int lognl)
 {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= words) return;
     const u64 q = T.mods[(gid / T.N) % K].q;
+    const size_t o = key_word_index(gid / T.N, gid % T.N, T.N, lognl);
     u64 rem = key[gid], quot = 0;
+    dkey[o] = rem;
 #pragma unroll 1
     for (int i = 0; i < 64; i++) {
         rem <<= 1;
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(256) k_shoup_quotients(Tables T, const u64 *__
             quot |= 1;
         }
     }
-    key_s[gid] = quot;
+    dkey[o + 2] = quot;
 }
 
 // ------------------------------------------------------------------------------------ K6 step 3 / K9
@@ -394,7 +413,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
     const u64 *ap = A.addend[p] ? A.addend[p] + (size_t)b * A.add_ct_stride + (size_t)j * N + off : nullptr;
     u64 *op = A.out + (size_t)b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + off;
     canon_all(x, m);
-    for_pairs_contig(tid, [&](int reg, int e) {
+    contig_to_co(x, sm, tid);
+    for_pairs_co(tid, [&](int reg, int e) {
         ulonglong2 bv = ldg2(bp + e);
         u64 u0 = x[reg], u1 = x[reg + 1];
         u64 v0 = shoup(sub_mod(bv.x, u0, m.q), qi.x, qi.y, m.q);

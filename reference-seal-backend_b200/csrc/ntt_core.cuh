@@ -327,6 +327,57 @@ template <class F> __device__ __forceinline__ void for_pairs_contig(int tid, F &
     for (int p = 0; p < 16; p += 2) f(p, 16 * tid + p);
 }
 
+// ---- contiguous layout <-> coalesced global access, through the warp's own slice of the transform buffer ----
+// In the contiguous layout a thread owns 16 adjacent coefficients (128 B), so a warp-wide 128-bit access touches
+// 32 different 128-byte lines and uses 16 bytes of each: 2x sector over-fetch on loads, partial-line writes, and
+// 8 dependent store instructions through one register quad.  A warp's 32 threads together own one contiguous
+// 4 KiB range (512 coefficients), which is exactly that warp's private slice of the swizzled transform buffer
+// (the last forward / first inverse pass touches no other slice), so an intra-warp transpose through it turns
+// the layout into the "lane-interleaved" one -- register pair i <-> coefficients co_elem(tid, i), +1 -- in which
+// every warp-wide access covers 512 contiguous bytes.  Both directions are bank-conflict free under swz().
+__device__ __forceinline__ void warp_sync()
+{
+#ifdef B200HE_EMU
+    __syncthreads();   // fibers: every thread of the block reaches this point (uniform control flow)
+#else
+    __syncwarp();
+#endif
+}
+__host__ __device__ __forceinline__ int co_elem(int tid, int i) { return ((tid >> 5) << 9) + (i << 6) + ((tid & 31) << 1); }
+// contiguous -> lane-interleaved.  The slice must be free (no pending reads of it by this warp's later code).
+__device__ __forceinline__ void contig_to_co(u64 (&x)[16], u64 *sm, int tid)
+{
+#pragma unroll
+    for (int p = 0; p < 8; p++) *reinterpret_cast<ulonglong2 *>(sm + swz(16 * tid + 2 * p)) = make_ulonglong2(x[2 * p], x[2 * p + 1]);
+    warp_sync();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sm + swz(co_elem(tid, i)));
+        x[2 * i] = v.x;
+        x[2 * i + 1] = v.y;
+    }
+}
+// lane-interleaved -> contiguous; ends with a warp_sync so the slice may be overwritten right away
+__device__ __forceinline__ void co_to_contig(u64 (&x)[16], u64 *sm, int tid)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) *reinterpret_cast<ulonglong2 *>(sm + swz(co_elem(tid, i))) = make_ulonglong2(x[2 * i], x[2 * i + 1]);
+    warp_sync();
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sm + swz(16 * tid + 2 * p));
+        x[2 * p] = v.x;
+        x[2 * p + 1] = v.y;
+    }
+    warp_sync();
+}
+// lane-interleaved layout: register pair (2i, 2i+1) <-> coefficients co_elem(tid, i), +1
+template <class F> __device__ __forceinline__ void for_pairs_co(int tid, F &&f)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) f(2 * i, co_elem(tid, i));
+}
+
 __device__ __forceinline__ ulonglong2 ldg2(const u64 *p)
 {
 #if defined(__CUDA_ARCH__)
