@@ -46,6 +46,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def butterfly_peak():
+    """register-resident 64-bit Shoup butterflies per second of the whole chip, measured by tools/imad_peak.cu on
+    this pool's B200 (profiles/r1d_imad_peak.json): the integer roofline of the NTT-bearing kernels"""
+    p = os.path.join(ROOT, "profiles", "r1d_imad_peak.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["bfly_exact_mulhi"]["Gbfly_per_s"] * 1e9, "measured (profiles/r1d_imad_peak.json)"
+    except Exception:
+        return 1.0e12, "fallback (DESIGN.md §3.1)"
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (NVML; nvidia-smi as a fallback)"""
 
@@ -115,15 +126,29 @@ def synth_inputs(moduli, n, L, N, seed):
     return out
 
 
+# butterfly-equivalents (one 64-bit Shoup multiply each) per launch of each NTT-bearing kernel class, averaged over
+# the launches of that class in one step
+def butterfly_equivalents(cls, B, L, K, N):
+    bf = (N // 2) * (N.bit_length() - 1)
+    return {
+        # L(L+1) forward NTTs minus the L reused NTT-form digits, 2 inverse NTTs (special-prime limb), 2 L (L+1) N MACs
+        "k_ks_inner": (L * (L + 1) - L + 2) * bf * B + 2 * L * (L + 1) * N * B,
+        # key-switch mod-down: 2L NTTs + 2L N scalings; rescale: 2(L-1) NTTs + 2(L-1) N scalings
+        "k_moddown": ((2 * L + 2 * (L - 1)) * bf + (2 * L + 2 * (L - 1)) * N) * B / 2.0,
+        "k_ntt_inv": (L + 2) * bf * B / 2.0,
+    }.get(cls)
+
+
 # per-launch algorithmic bytes of each kernel class for this workload (DESIGN.md "Kernels"), W = 8 B
 def algorithmic_bytes(cls, B, L, K, N):
     W = 8
     return {
         "k_tensor": (4 + 3) * L * N * W * B,
-        # three k_ntt_inv launches per step: L limbs (target), 2 (special-prime accumulators), 2 (rescale last limb)
-        "k_ntt_inv": 2 * N * W * B * (L + 2 + 2) / 3.0,
-        # reads target coeff + NTT form, writes 2(L+1) accumulator limbs; key read once per launch
-        "k_ks_inner": (2 * L + 2 * (L + 1)) * N * W * B + 2 * L * (L + 1) * N * W,
+        # two k_ntt_inv launches per step: L limbs (relinearization target), 2 (last limb of the rescale input)
+        "k_ntt_inv": 2 * N * W * B * (L + 2) / 2.0,
+        # reads target in coefficient + NTT form, writes 2L accumulator limbs and the 2 rounded special-prime limbs;
+        # key (with Shoup quotients) read once per launch
+        "k_ks_inner": (2 * L + 2 * (L + 1)) * N * W * B + 4 * L * (L + 1) * N * W,
         # two launches per step: key-switch mod-down (rp 2, acc 2L, addend 2L, out 2L) and rescale (rp 2, in 2(L-1), out 2(L-1))
         "k_moddown": ((2 + 6 * L) + (2 + 4 * (L - 1))) * N * W * B / 2.0,
     }.get(cls)
@@ -143,10 +168,13 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    from pyb200he.shard import Ranks
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ranks = Ranks(dist, device=torch.device("cuda", local))
 
     host = Host(CKKS, N_POLY, DEPTH, COEFF_BITS, COEFF_BITS, seed=SEED)
     ctx = hb.Context(CKKS, N_POLY, host.moduli, host.psi, 0, device=local)
@@ -178,7 +206,7 @@ def run_b200(args):
 
     # end-to-end leg: the batch is cut into chunks that travel through E2E_STREAMS contexts (one stream each), so
     # the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap on the PCIe/compute engines
-    E2E_STREAMS, CHUNK = 3, 125
+    E2E_STREAMS, CHUNK = 3, 50
     e2e = []
     for i in range(E2E_STREAMS):
         cx = hb.Context(CKKS, N_POLY, host.moduli, host.psi, 0, device=local)
@@ -188,6 +216,7 @@ def run_b200(args):
         bufs = [hb.Batch(cx), hb.Batch(cx), hb.Batch(cx)]
         bufs[0].resize(CHUNK, 2, L, True, scale)
         bufs[1].resize(CHUNK, 2, L, True, scale)
+        bufs[2].resize(CHUNK, 3, L, True, scale)   # sized for the largest intermediate (the size-3 product)
         e2e.append((cx, st, bufs))
 
     def e2e_step():
@@ -204,16 +233,10 @@ def run_b200(args):
             cx.sync()   # results are on the host
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        ranks.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = ranks.max_over_ranks
 
     upload()
     ctx.sync()
@@ -279,20 +302,27 @@ def run_b200(args):
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(top_name)
-    ntt_limbs = {"k_ks_inner": 4, "k_moddown": 3, "k_ntt_inv": (L + 4) / 3.0}.get(top_name, 0) * BATCH
+    ntt_limbs = {"k_ks_inner": 6, "k_moddown": 3, "k_ntt_inv": (L + 2) / 2.0}.get(top_name, 0) * BATCH
+    bfe = butterfly_equivalents(top_name, BATCH, L, K, N)
+    bf_peak, bf_src = butterfly_peak()
+    bf_rate = bfe / (top_ms / top_n / 1e3) if bfe else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic (uniform random residues, seed 1234; real relinearization key)",
         "config": CONFIG, "clocks": clocks,
-        "e2e": {"value": samples / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * words_in * 8,
-                "d2h_bytes_per_step": BATCH * words_out * 8, "ms_per_step": e2e_ms / args.steps,
+        "e2e": {"value": samples / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * words_in * 8 * world,
+                "d2h_bytes_per_step": BATCH * words_out * 8 * world, "ms_per_step": e2e_ms / args.steps,
                 "pipeline": f"{E2E_STREAMS} streams x chunks of {CHUNK} ciphertext pairs"},
-        "gpu_launches": launches,
+        "gpu_launches": launches * world,
         "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": top_ms / top_n, "share_of_step": top_ms / (ms_total_local(prof)),
-                     "limb_ntts_per_s": ntt_limbs / (top_ms / top_n / 1e3) if ntt_limbs else None},
+                     "limb_ntts_per_s": ntt_limbs / (top_ms / top_n / 1e3) if ntt_limbs else None,
+                     # the NTT-bearing kernels are bound by the integer (fma) pipe, not HBM: fraction of the measured
+                     # register-resident 64-bit butterfly rate of the chip
+                     "int_pipe": {"achieved": bf_rate, "peak": bf_peak, "unit": "butterflies/s",
+                                  "frac": (bf_rate / bf_peak) if bf_rate else None, "peak_source": bf_src}},
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
     }
     line["cpu_baseline"] = cpu_baseline(budget_s=12.0) if world == 1 else None

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (from gpurun_out/) into profiles/: per-launch table of the metrics the roofline
-uses.  Usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_ncu_full.md"""
+uses.  Usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_ncu_full.md [profiles/traffic.json]"""
 import csv
 import io
 import subprocess
@@ -52,6 +52,19 @@ def main():
         f.write(f"ncu --set full --clock-control none summary of {rep} (one row per captured launch)\n\n")
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    if len(sys.argv) > 3:
+        # DRAM bytes (read + write) per launch, averaged per kernel class: bench.py's roofline.traffic
+        import json
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        acc = {}
+        for r in rows[2:]:
+            name = r[ki].split("(")[0].replace("void ", "").replace("b200he::", "").split("<")[0]
+            b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+            acc.setdefault(name, []).append(b)
+        with open(sys.argv[3], "w") as f:
+            json.dump({"source": rep, "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), mean over captured launches",
+                       **{k: sum(v) / len(v) for k, v in acc.items()}}, f, indent=1)
 
 
 if __name__ == "__main__":
