@@ -133,9 +133,10 @@ def butterfly_equivalents(cls, B, L, K, N):
     return {
         # L(L+1) forward NTTs minus the L reused NTT-form digits, 2 inverse NTTs (special-prime limb), 2 L (L+1) N MACs
         "k_ks_inner": (L * (L + 1) - L + 2) * bf * B + 2 * L * (L + 1) * N * B,
-        # key-switch mod-down: 2L NTTs + 2L N scalings; rescale: 2(L-1) NTTs + 2(L-1) N scalings
-        "k_moddown": ((2 * L + 2 * (L - 1)) * bf + (2 * L + 2 * (L - 1)) * N) * B / 2.0,
-        "k_ntt_inv": (L + 2) * bf * B / 2.0,
+        # fused relinearize+rescale mod-down of the L-1 surviving limbs: 2(L-1) NTTs + 4 Shoup scalings per coefficient
+        "k_moddown": (2 * (L - 1) * bf + 8 * (L - 1) * N) * B,
+        # two launches: the relinearization target (L limbs) and the fused last limb (2 limbs + 2 scalings per coefficient)
+        "k_ntt_inv": ((L + 2) * bf + 4 * N) * B / 2.0,
     }.get(cls)
 
 
@@ -144,13 +145,15 @@ def algorithmic_bytes(cls, B, L, K, N):
     W = 8
     return {
         "k_tensor": (4 + 3) * L * N * W * B,
-        # two k_ntt_inv launches per step: L limbs (relinearization target), 2 (last limb of the rescale input)
-        "k_ntt_inv": 2 * N * W * B * (L + 2) / 2.0,
+        # two k_ntt_inv launches per step: relinearization target (L limbs in, L out) and the fused last limb
+        # (accumulator, input ciphertext and rounded special-prime limb in, rounded last limb out; 2 polys)
+        "k_ntt_inv": (2 * L + 8) * N * W * B / 2.0,
         # reads target in coefficient + NTT form, writes 2L accumulator limbs and the 2 rounded special-prime limbs;
         # key (with Shoup quotients) read once per launch
         "k_ks_inner": (2 * L + 2 * (L + 1)) * N * W * B + 4 * L * (L + 1) * N * W,
-        # two launches per step: key-switch mod-down (rp 2, acc 2L, addend 2L, out 2L) and rescale (rp 2, in 2(L-1), out 2(L-1))
-        "k_moddown": ((2 + 6 * L) + (2 + 4 * (L - 1))) * N * W * B / 2.0,
+        # one launch per step (fused relinearize+rescale): both rounded limbs (2 + 2), then per surviving limb and poly the
+        # accumulator, the input ciphertext limb and the output
+        "k_moddown": (4 + 6 * (L - 1)) * N * W * B,
     }.get(cls)
 
 
@@ -201,8 +204,7 @@ def run_b200(args):
 
     def step():
         ctx.multiply(A, B, out=R)
-        ctx.relinearize(R, out=R)
-        ctx.rescale_to_next(R, out=R)
+        ctx.relinearize_rescale(R, out=R)   # relinearize_inplace + rescale_to_next_inplace, bit-identical, one fused entry
 
     # end-to-end leg: the batch is cut into chunks that travel through E2E_STREAMS contexts (one stream each), so
     # the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap on the PCIe/compute engines
@@ -226,8 +228,7 @@ def run_b200(args):
             ca.upload_from(a_pin.data_ptr() + first * words_in * 8, 0, n)
             cb.upload_from(b_pin.data_ptr() + first * words_in * 8, 0, n)
             cx.multiply(ca, cb, n=n, out=cr)
-            cx.relinearize(cr, out=cr)
-            cx.rescale_to_next(cr, out=cr)
+            cx.relinearize_rescale(cr, out=cr)
             cr.download_to(out_pin.data_ptr() + first * words_out * 8, 0, n, wait=False)
         for cx, st, _ in e2e:
             cx.sync()   # results are on the host
@@ -280,7 +281,7 @@ def run_b200(args):
 
     # sanity: the timed path produced the bits the step defines (first result vs a fresh single-ciphertext run)
     chk = ctx.multiply(ctx.batch(a_np[:1], scale=scale), ctx.batch(b_np[:1], scale=scale))
-    ctx.relinearize(chk, out=chk)
+    ctx.relinearize(chk, out=chk)        # the two separate calls: the fused entry must give the same bits
     ctx.rescale_to_next(chk, out=chk)
     got = out_pin.numpy()[:words_out].view(np.uint64)
     assert np.array_equal(got, chk.download().reshape(-1)), "timed path result differs from a fresh evaluation"
@@ -302,7 +303,7 @@ def run_b200(args):
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(top_name)
-    ntt_limbs = {"k_ks_inner": 6, "k_moddown": 3, "k_ntt_inv": (L + 2) / 2.0}.get(top_name, 0) * BATCH
+    ntt_limbs = {"k_ks_inner": L * L + 2, "k_moddown": 2 * (L - 1), "k_ntt_inv": (L + 2) / 2.0}.get(top_name, 0) * BATCH
     bfe = butterfly_equivalents(top_name, BATCH, L, K, N)
     bf_peak, bf_src = butterfly_peak()
     bf_rate = bfe / (top_ms / top_n / 1e3) if bfe else None

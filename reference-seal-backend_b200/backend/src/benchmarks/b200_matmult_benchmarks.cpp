@@ -249,12 +249,14 @@ template <bool CKKS> ShardedCiphertexts MatMultBenchmarkT<CKKS>::operateVal(cons
         DeviceBatchPtr r = cw.newBatch(g);
         cw.check(b200he_multiply(c, in[0].shard[g]->get(), ai.data(), in[1].shard[g]->get(), bi.data(), n, r->get()), "b200he_multiply");
         if (n > 0) {
-            cw.check(b200he_relinearize(c, r->get(), r->get()), "b200he_relinearize");
             if (CKKS) {
-                cw.check(b200he_rescale_to_next(c, r->get(), r->get()), "b200he_rescale_to_next");
+                // relinearize_inplace + rescale_to_next_inplace (R/src/benchmarks/ckks/seal_ckks_matmultval_benchmark.cpp:252-255): fused, same bits
+                cw.check(b200he_relinearize_rescale(c, r->get(), r->get()), "b200he_relinearize_rescale");
                 cw.accumulateCKKS(*r, c0);
-            } else
+            } else {
+                cw.check(b200he_relinearize(c, r->get(), r->get()), "b200he_relinearize");
                 cw.accumulateBFV(*r, c0);
+            }
         }
         out.shard.push_back(r);
     }
@@ -316,8 +318,7 @@ template <bool CKKS> ShardedCiphertexts MatMultBenchmarkT<CKKS>::operateCipherBa
             if (k > 0) cw.check(b200he_add(c, acc->get(), nullptr, prod->get(), nullptr, n, acc->get()), "b200he_add");
         }
         if (CKKS && n > 0) {
-            cw.check(b200he_relinearize(c, acc->get(), acc->get()), "b200he_relinearize");
-            cw.check(b200he_rescale_to_next(c, acc->get(), acc->get()), "b200he_rescale_to_next");
+            cw.check(b200he_relinearize_rescale(c, acc->get(), acc->get()), "b200he_relinearize_rescale");
         }
         out.shard.push_back(acc);
     }

@@ -280,8 +280,8 @@ DeviceBatchPtr SEALContextWrapper::collapseCKKS(DeviceBatch &ciphers, std::size_
         check(b200he_rotate_each(c, ciphers.get(), steps.data(), ciphers.get()), "b200he_rotate_each");
         DeviceBatchPtr masks = maskBatch(g, first_index, n, total, ciphers.level());
         check(b200he_multiply_plain(c, ciphers.get(), masks->get(), nullptr, ciphers.get()), "b200he_multiply_plain");
-        check(b200he_relinearize(c, ciphers.get(), ciphers.get()), "b200he_relinearize");   // size 2: no-op, as in the reference
-        check(b200he_rescale_to_next(c, ciphers.get(), ciphers.get()), "b200he_rescale_to_next");
+        // relinearize_inplace (size 2: no-op, as in the reference) + rescale_to_next_inplace
+        check(b200he_relinearize_rescale(c, ciphers.get(), ciphers.get()), "b200he_relinearize_rescale");
         check(b200he_batch_set_scale(ciphers.get(), m_scale), "b200he_batch_set_scale");
         check(b200he_sum(c, ciphers.get(), result->get()), "b200he_sum");
     }
@@ -313,8 +313,7 @@ DeviceBatchPtr SEALContextWrapper::evaluatePolynomial(DeviceBatch &cipher_input,
     for (++it; it != plain_coefficients.rend(); ++it) {
         matchLevel(cipher_input, *retval);
         check(b200he_multiply(c, retval->get(), nullptr, cipher_input.get(), nullptr, 1, retval->get()), "b200he_multiply");
-        check(b200he_relinearize(c, retval->get(), retval->get()), "b200he_relinearize");
-        check(b200he_rescale_to_next(c, retval->get(), retval->get()), "b200he_rescale_to_next");
+        check(b200he_relinearize_rescale(c, retval->get(), retval->get()), "b200he_relinearize_rescale");
         Plaintext p = *it;   // mod_switch_to_inplace(plain, retval.parms_id())
         p.data.resize((std::size_t)retval->level() * m_N);
         p.L = retval->level();

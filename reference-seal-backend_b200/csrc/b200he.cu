@@ -597,15 +597,18 @@ static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_
     LAUNCH_CHECK();
     return 0;
 }
-static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base, int mode)
+static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base, int mode,
+                   const InvFuse *fuse = nullptr)
 {
     if (!nlimbs) return 0;
+    InvFuse F{};
+    if (fuse) F = *fuse;
     NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_NTT_INV, k_ntt_inv<LG>, (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                           c->T, src, dst, src_outer, dst_outer, L, mod_base, c->c, mode));
+                           c->T, src, dst, src_outer, dst_outer, L, mod_base, c->c, mode, F));
     LAUNCH_CHECK();
     if (c->c > 0) {
         const size_t threads = nlimbs * ((size_t)c->N >> c->c) / 2;
-        LAUNCH(c, B200HE_KERN_NTT_INV_TAIL, k_ntt_inv_tail, blocks_for(threads), 256, 0, c->T, dst, dst_outer, nlimbs, L, mod_base, c->c, mode);
+        LAUNCH(c, B200HE_KERN_NTT_INV_TAIL, k_ntt_inv_tail, blocks_for(threads), 256, 0, c->T, dst, dst_outer, nlimbs, L, mod_base, c->c, mode, F);
         LAUNCH_CHECK();
     }
     return 0;
@@ -803,13 +806,20 @@ extern "C" int b200he_gather(b200he_ctx *c, const b200he_batch *in, const uint32
 //   target: [L][N] per ciphertext (stride t_stride), NTT form (CKKS) or coefficient form (BFV)
 //   add0/add1: per-ciphertext addends (stride add_stride) or nullptr (zero)
 //   out: [2][L][N] per ciphertext (stride out_stride); out may alias add0/add1 element-for-element
+//
+// rescale = true (CKKS, add0/add1 required, L >= 2): out[b] = rescale_to_next((add0[b], add1[b]) + KeySwitch(target[b])),
+// [2][L-1][N] per ciphertext -- SEAL's relinearize_inplace followed by rescale_to_next_inplace, bit for bit, with
+// 2 + 2(L-1) transforms where the two separate calls need 2L + 2 + 2(L-1): every step is exact arithmetic in Z_q and
+// the transform is linear, so the last limb's mod-down correction is applied in coefficient form (InvFuse) and the two
+// corrections of each remaining limb share one transform (PreTwo).
 static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t t_stride, const u64 *key, const u64 *add0, const u64 *add1,
-                      size_t add_stride, u64 *out, size_t out_stride)
+                      size_t add_stride, u64 *out, size_t out_stride, bool rescale = false)
 {
     const size_t N = c->N, K = c->K;
     const bool ckks = c->scheme == B200HE_CKKS;
-    // scratch per ciphertext: tcoef [L][N] (CKKS), acc [2][L+1][N], rp [2][N]
-    const size_t w_t = ckks ? (size_t)L * N : 0, w_acc = 2 * (size_t)(L + 1) * N, w_rp = 2 * N;
+    if (rescale && (!ckks || !add0 || !add1 || L < 2)) return fail("key_switch: fused rescale needs CKKS, both addends and L >= 2");
+    // scratch per ciphertext: tcoef [L][N] (CKKS), acc [2][L+1][N], rp [2][N] (+ rp2 [2][N] for the fused rescale)
+    const size_t w_t = ckks ? (size_t)L * N : 0, w_acc = 2 * (size_t)(L + 1) * N, w_rp = rescale ? 4 * N : 2 * N;
     const size_t per_ct = (w_t + w_acc + w_rp) * 8;
     size_t chunk = c->workspace / per_ct;
     if (chunk < 1) chunk = 1;
@@ -845,7 +855,19 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
         D.add_ct_stride = add_stride;
         D.out = out + b0 * out_stride; D.out_ct_stride = out_stride; D.out_poly_stride = (size_t)L * N;
         D.P = 2; D.nJ = L; D.x = (int)K - 1;
-        if (ckks) {
+        if (rescale) {
+            // last data limb: rp2 = iNTT(acc * s + addend) - u1 * s + q/2   (rounded last limb of the switched ciphertext)
+            u64 *rp2 = rp + nb * 2 * N;
+            InvFuse F{};
+            F.add = add0 + b0 * add_stride + (size_t)(L - 1) * N;
+            F.add_ct_stride = add_stride; F.add_poly_stride = (size_t)(add1 - add0);
+            F.sub = rp; F.P = 2; F.x = (int)K - 1;
+            rc = ntt_inv(c, acc + (size_t)(L - 1) * N, rp2, nb * 2, (size_t)(L + 1) * N, N, 1, L - 1, INV_ADDHALF, &F);
+            if (rc) break;
+            D.rp2 = rp2; D.x2 = L - 1; D.nJ = L - 1; D.out_poly_stride = (size_t)(L - 1) * N;
+            NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown<LG>, (unsigned)((nb * 2 * (L - 1)) << c->c), NttCfg<LG>::THREADS,
+                                   NttCfg<LG>::SMEM_BYTES, c->T, D, c->c));
+        } else if (ckks) {
             NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown<LG>, (unsigned)((nb * 2 * L) << c->c), NttCfg<LG>::THREADS,
                                    NttCfg<LG>::SMEM_BYTES, c->T, D, c->c));
         } else {
@@ -877,6 +899,31 @@ extern "C" int b200he_relinearize(b200he_ctx *c, const b200he_batch *in, b200he_
     TRY(ob.shape(in->count, 2, in->L, in->ntt, in->scale));
     const size_t LN = (size_t)in->L * c->N;
     TRY(key_switch(c, in->L, in->count, in->d + 2 * LN, 3 * LN, c->relin, in->d, in->d + LN, 3 * LN, ob.ptr(), 2 * LN));
+    ob.commit();
+    return 0;
+}
+
+// relinearize_inplace immediately followed by rescale_to_next_inplace, as every multiply of the CKKS matmul and
+// logistic-regression workloads does (R/src/benchmarks/ckks/seal_ckks_matmultval_benchmark.cpp:252-255,
+// R/src/engine/seal_context.cpp:390-391,447-448): same bits as the two calls, fewer transforms (see key_switch).
+extern "C" int b200he_relinearize_rescale(b200he_ctx *c, const b200he_batch *in, b200he_batch *out)
+{
+    if (!c || !in || !out) return fail("relinearize_rescale: NULL argument");
+    if (in->ctx != c || out->ctx != c) return fail("relinearize_rescale: batch belongs to another context");
+    if (c->scheme != B200HE_CKKS || in->size != 3) {   // BFV, or nothing to relinearize: the two plain calls
+        TRY(b200he_relinearize(c, in, out));
+        return b200he_rescale_to_next(c, out, out);
+    }
+    if (in->L < 2) return fail("rescale: already at the last level");
+    if (!c->relin) return fail("relinearize: no relinearization key uploaded");
+    if (!in->ntt) return fail("relinearize: wrong NTT form for scheme");
+    CK(cudaSetDevice(c->device));
+    const int L = in->L;
+    OutBuf ob(out, in);
+    TRY(ob.shape(in->count, 2, L - 1, 1, in->scale / (double)c->mods[L - 1].q));
+    const size_t LN = (size_t)L * c->N;
+    if (in->count)
+        TRY(key_switch(c, L, in->count, in->d + 2 * LN, 3 * LN, c->relin, in->d, in->d + LN, 3 * LN, ob.ptr(), 2 * (size_t)(L - 1) * c->N, true));
     ob.commit();
     return 0;
 }

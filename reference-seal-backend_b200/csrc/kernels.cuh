@@ -41,16 +41,35 @@ __device__ __forceinline__ u64 *dyn_smem()
 #endif
 }
 
-// Input transforms fused into the first-pass load.
-struct PreNone { __device__ __forceinline__ u64 operator()(u64 v) const { return v; } };
+// Input transforms fused into the first-pass load: pair(v, idx) maps the coefficient pair at limb index idx, idx+1.
+struct PreNone { __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return v; } };
 struct PreReduce {   // v mod q (lift of a digit into another modulus, SEAL modulo_poly_coeffs)
     Mod m;
-    __device__ __forceinline__ u64 operator()(u64 v) const { return reduce64(v, m); }
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64(v.x, m), reduce64(v.y, m)); }
 };
 struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_last/2 mod q))
     Mod m;
     u64 fix;
-    __device__ __forceinline__ u64 operator()(u64 v) const { return reduce64(v, m) + fix; }
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64(v.x, m) + fix, reduce64(v.y, m) + fix); }
+};
+// Fused relinearize + rescale (k_moddown with two rounded limbs): the two mod-down corrections of output limb j,
+// NTT(u1) * s * r (key switch, s = q_sp^{-1}) and NTT(u2) * r (rescale, r = q_last^{-1}), are one transform of
+// (u1 * s + u2) * r because the transform is linear over Z_q.  Result in [0, 2q).
+struct PreTwo {
+    Mod m;
+    u64 fix1, fix2;
+    ulonglong2 s, r;
+    const u64 *rp2;
+    __device__ __forceinline__ u64 one(u64 v1, u64 v2) const
+    {
+        const u64 a = shoup_lazy(reduce64(v1, m) + fix1, s.x, s.y, m.q);
+        return shoup_lazy(a + reduce64(v2, m) + fix2, r.x, r.y, m.q);
+    }
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t idx) const
+    {
+        const ulonglong2 w = ldg2(rp2 + idx);
+        return make_ulonglong2(one(v.x, w.x), one(v.y, w.y));
+    }
 };
 
 // lazy Cooley-Tukey butterfly used by the split pre-stages (bound of both outputs: bound(a) + 2q)
@@ -71,15 +90,15 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
     constexpr int NL = 1 << LOGN;
     if (c == 0) {
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            ulonglong2 v = ldg2(src + e);
-            x[reg] = pre(v.x);
-            x[reg + 1] = pre(v.y);
+            const ulonglong2 v = pre.pair(ldg2(src + e), e);
+            x[reg] = v.x;
+            x[reg + 1] = v.y;
         });
     } else if (c == 1) {
         const ulonglong2 w = ld_tw(tw + 1);
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            ulonglong2 a = ldg2(src + e), b = ldg2(src + e + NL);
-            u64 a0 = pre(a.x), a1 = pre(a.y), b0 = pre(b.x), b1 = pre(b.y);
+            const ulonglong2 a = pre.pair(ldg2(src + e), e), b = pre.pair(ldg2(src + e + NL), e + NL);
+            u64 a0 = a.x, a1 = a.y, b0 = b.x, b1 = b.y;
             ct_lazy(a0, b0, w, m);
             ct_lazy(a1, b1, w, m);
             x[reg] = r ? b0 : a0;
@@ -88,10 +107,11 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
     } else {
         const ulonglong2 w1 = ld_tw(tw + 1), w2 = ld_tw(tw + 2 + (r >> 1));
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            ulonglong2 v0 = ldg2(src + e), v1 = ldg2(src + e + NL), v2 = ldg2(src + e + 2 * NL), v3 = ldg2(src + e + 3 * NL);
+            const ulonglong2 v0 = pre.pair(ldg2(src + e), e), v1 = pre.pair(ldg2(src + e + NL), e + NL),
+                             v2 = pre.pair(ldg2(src + e + 2 * NL), e + 2 * NL), v3 = pre.pair(ldg2(src + e + 3 * NL), e + 3 * NL);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                u64 a0 = pre(h ? v0.y : v0.x), a1 = pre(h ? v1.y : v1.x), a2 = pre(h ? v2.y : v2.x), a3 = pre(h ? v3.y : v3.x);
+                u64 a0 = h ? v0.y : v0.x, a1 = h ? v1.y : v1.x, a2 = h ? v2.y : v2.x, a3 = h ? v3.y : v3.x;
                 ct_lazy(a0, a2, w1, m);
                 ct_lazy(a1, a3, w1, m);
                 u64 u = (r >> 1) ? a2 : a0, v = (r >> 1) ? a3 : a1;
@@ -136,10 +156,27 @@ __device__ __forceinline__ u64 inv_finish(u64 v /* [0,2q) */, const Mod &m, int 
     if (mode == INV_ADDHALF) v = csub(v + (m.q >> 1), m.q);
     return v;
 }
+// Optional fusion around the inverse transform of limb w = (b, p) (b = w / P, p = w % P), used by the fused
+// relinearize + rescale for the last data limb j:
+//   input   y = src * s + add[b][p]          (s = q_x^{-1} mod q_j: the key-switch accumulator scaled and added to the
+//                                             input ciphertext, still in NTT form)
+//   output  iNTT(y) - ((sub[w] mod q_j) + fix) * s   (the mod-down correction applied in coefficient form: the
+//                                             transform is linear, so NTT(u) never has to be computed for this limb)
+// followed by the usual finish (INV_ADDHALF: + q_j / 2, the rounding of the rescale that follows).
+struct InvFuse {
+    const u64 *add;        // nullptr: plain transform
+    size_t add_ct_stride, add_poly_stride;
+    const u64 *sub;        // [nlimbs][N] coefficient form (the rounded special-prime limb)
+    int P, x;              // polys per ciphertext; x = modulus id of the prime dropped by the key switch
+};
+__device__ __forceinline__ u64 inv_post(u64 v /* finished, canonical */, u64 subv, const Mod &m, ulonglong2 s, u64 fix)
+{
+    return sub_mod(v, shoup(reduce64(subv, m) + fix, s.x, s.y, m.q), m.q);
+}
 // c == 0: dst = iNTT(src) (finished).  c > 0: dst = partial (local stages only, values in [0,2q)).
 template <int LOGN>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
-                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base, int c, int mode)
+                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base, int c, int mode, InvFuse F)
 {
     constexpr int NL = 1 << LOGN;
     u64 *sm = dyn_smem();
@@ -152,15 +189,37 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     u64 x[16];
     TwRegs<LOGN, Sched<LOGN>::NP - 1> tl;
     load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, (1 << c) + r);
-    for_pairs_co(tid, [&](int reg, int e) {
-        ulonglong2 v = ldg2(in + e);
-        x[reg] = v.x;
-        x[reg + 1] = v.y;
-    });
+    ulonglong2 fs = make_ulonglong2(0, 0);
+    u64 ffix = 0;
+    if (F.add) {
+        fs = T.qinv[(size_t)F.x * T.M + mid];
+        ffix = m.q - T.halfmod[(size_t)F.x * T.M + mid];
+        const u64 *ad = F.add + (size_t)(w / F.P) * F.add_ct_stride + (size_t)(w % F.P) * F.add_poly_stride + (size_t)r * NL;
+        for_pairs_co(tid, [&](int reg, int e) {
+            const ulonglong2 v = ldg2(in + e), a = ldg2(ad + e);
+            x[reg] = add_mod(shoup(v.x, fs.x, fs.y, m.q), a.x, m.q);
+            x[reg + 1] = add_mod(shoup(v.y, fs.x, fs.y, m.q), a.y, m.q);
+        });
+    } else {
+        for_pairs_co(tid, [&](int reg, int e) {
+            ulonglong2 v = ldg2(in + e);
+            x[reg] = v.x;
+            x[reg + 1] = v.y;
+        });
+    }
     co_to_contig(x, sm, tid);
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     if (c == 0) {
         ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0, tl);
+        if (F.add) {
+            const u64 *sb = F.sub + (size_t)w * T.N;
+            for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+                const ulonglong2 u = ldg2(sb + e);
+                const u64 v0 = inv_post(csub(x[reg], m.q), u.x, m, fs, ffix), v1 = inv_post(csub(x[reg + 1], m.q), u.y, m, fs, ffix);
+                st2(out + e, mode == INV_ADDHALF ? csub(v0 + (m.q >> 1), m.q) : v0, mode == INV_ADDHALF ? csub(v1 + (m.q >> 1), m.q) : v1);
+            });
+            return;
+        }
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, mode), inv_finish(x[reg + 1], m, mode)); });
     } else {
         ntt_inv_regs_split<LOGN, false>(x, sm, itw, m, tid, c, r, tl);
@@ -170,7 +229,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
 }
 // Tail of a split inverse: the last c Gentleman-Sande stages across the 2^c chunks, N^{-1}, finish.
 // One thread per coefficient pair of a chunk; in place.  grid covers nlimbs * (N >> c) / 2 threads.
-__global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict__ data, size_t outer, size_t nlimbs, int L, int mod_base, int c, int mode)
+__global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict__ data, size_t outer, size_t nlimbs, int L, int mod_base, int c, int mode,
+                                                      InvFuse F)
 {
     const size_t chunk = (size_t)T.N >> c, per_limb = chunk / 2;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,11 +241,26 @@ __global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict_
     const ulonglong2 *itw = T.itw + (size_t)mid * T.N;
     u64 *p = data + (w / L) * outer + (w % L) * T.N + e;
     const ulonglong2 wn = ld_tw(itw);
+    // finish of output pair k (limb index e + k * chunk): canonical value, fused mod-down correction, rounding
+    ulonglong2 fs = make_ulonglong2(0, 0);
+    u64 ffix = 0;
+    if (F.add) {
+        fs = T.qinv[(size_t)F.x * T.M + mid];
+        ffix = m.q - T.halfmod[(size_t)F.x * T.M + mid];
+    }
+    auto fin = [&](u64 lazy0, u64 lazy1, int k) {
+        if (!F.add) return make_ulonglong2(inv_finish(lazy0, m, mode), inv_finish(lazy1, m, mode));
+        const ulonglong2 u = ld2(F.sub + w * T.N + e + (size_t)k * chunk);
+        const u64 v0 = inv_post(csub(lazy0, m.q), u.x, m, fs, ffix), v1 = inv_post(csub(lazy1, m.q), u.y, m, fs, ffix);
+        return make_ulonglong2(mode == INV_ADDHALF ? csub(v0 + (m.q >> 1), m.q) : v0, mode == INV_ADDHALF ? csub(v1 + (m.q >> 1), m.q) : v1);
+    };
     if (c == 1) {
         ulonglong2 a = ld2(p), b = ld2(p + chunk);
         u64 s0 = a.x + b.x, d0 = a.x - b.x + m.two_q, s1 = a.y + b.y, d1 = a.y - b.y + m.two_q;
-        st2(p, inv_finish(shoup_lazy(s0, m.ninv, m.ninv_s, m.q), m, mode), inv_finish(shoup_lazy(s1, m.ninv, m.ninv_s, m.q), m, mode));
-        st2(p + chunk, inv_finish(shoup_lazy(d0, wn.x, wn.y, m.q), m, mode), inv_finish(shoup_lazy(d1, wn.x, wn.y, m.q), m, mode));
+        const ulonglong2 o0 = fin(shoup_lazy(s0, m.ninv, m.ninv_s, m.q), shoup_lazy(s1, m.ninv, m.ninv_s, m.q), 0);
+        const ulonglong2 o1 = fin(shoup_lazy(d0, wn.x, wn.y, m.q), shoup_lazy(d1, wn.x, wn.y, m.q), 1);
+        st2(p, o0.x, o0.y);
+        st2(p + chunk, o1.x, o1.y);
     } else {
         ulonglong2 v[4];
 #pragma unroll
@@ -203,7 +278,10 @@ __global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict_
             o[3][h] = shoup_lazy(a1 - a3 + m.two_q, wn.x, wn.y, m.q);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) st2(p + k * chunk, inv_finish(o[k][0], m, mode), inv_finish(o[k][1], m, mode));
+        for (int k = 0; k < 4; k++) {
+            const ulonglong2 ov = fin(o[k][0], o[k][1], k);
+            st2(p + k * chunk, ov.x, ov.y);
+        }
     }
 }
 
@@ -387,6 +465,10 @@ struct ModDownArgs {
     u64 *out;              // out + b*out_ct_stride + p*out_poly_stride + j*N
     size_t out_ct_stride, out_poly_stride;
     int P, nJ, x;          // x = modulus id of the dropped prime
+    // fused relinearize + rescale: rp2 = rounded last data limb (coefficient form, [B][P][N]) of the key-switched
+    // ciphertext, x2 = its modulus id.  out = (base * s + addend) * r - NTT((u1 * s + u2) * r), s = q_x^{-1}, r = q_x2^{-1}
+    const u64 *rp2;
+    int x2;
 };
 template <int LOGN>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, ModDownArgs A, int c)
@@ -407,11 +489,27 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
     u64 x[16];
     TwRegs<LOGN, 0> t0;
     load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
-    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m, fix });
-    ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     const u64 *bp = A.base + (size_t)b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + off;
     const u64 *ap = A.addend[p] ? A.addend[p] + (size_t)b * A.add_ct_stride + (size_t)j * N + off : nullptr;
     u64 *op = A.out + (size_t)b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + off;
+    if (A.rp2) {
+        const ulonglong2 ri = T.qinv[(size_t)A.x2 * T.M + j];
+        const u64 fix2 = m.q - T.halfmod[(size_t)A.x2 * T.M + j];
+        load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
+                             PreTwo{ m, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N });
+        ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
+        canon_all(x, m);
+        contig_to_co(x, sm, tid);
+        for_pairs_co(tid, [&](int reg, int e) {
+            const ulonglong2 bv = ldg2(bp + e), av = ldg2(ap + e);
+            const u64 g0 = shoup_lazy(bv.x, qi.x, qi.y, m.q) + av.x, g1 = shoup_lazy(bv.y, qi.x, qi.y, m.q) + av.y;   // < 3q
+            const u64 h0 = shoup(g0, ri.x, ri.y, m.q), h1 = shoup(g1, ri.x, ri.y, m.q);
+            st2(op + e, sub_mod(h0, x[reg], m.q), sub_mod(h1, x[reg + 1], m.q));
+        });
+        return;
+    }
+    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m, fix });
+    ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     canon_all(x, m);
     contig_to_co(x, sm, tid);
     for_pairs_co(tid, [&](int reg, int e) {

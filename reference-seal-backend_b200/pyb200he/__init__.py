@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200he_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200he_apply_galois": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200he_rescale_to_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200he_relinearize_rescale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200he_mod_drop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200he_multiply_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u32p, C.c_void_p]),
     "b200he_add_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u32p, C.c_void_p]),
@@ -283,6 +284,9 @@ class Context:
 
     def rescale_to_next(self, a, out=None):
         return self._unary(self.lib.b200he_rescale_to_next, a, out)
+
+    def relinearize_rescale(self, a, out=None):
+        return self._unary(self.lib.b200he_relinearize_rescale, a, out)
 
     def mod_drop(self, a, L_target, out=None):
         return self._unary(self.lib.b200he_mod_drop, a, out, int(L_target))

@@ -223,6 +223,25 @@ def case_mul_relin_rescale(env, n=3):
     eq(r.download(), want, "multiply+relinearize+rescale")
 
 
+def case_relin_rescale_fused(env, n=3, L=None):
+    """b200he_relinearize_rescale == relinearize_inplace then rescale_to_next_inplace, bit for bit, and == the two
+    separate C-ABI calls"""
+    L = env.Ltop if L is None else L
+    ct3 = env.rand_ct(n, size=3, L=L)
+    b = env.batch(ct3, size=3, L=L, scale=2.0 ** 80)
+    fused = env.ctx.relinearize_rescale(b)
+    assert fused.L == L - 1 and fused.size == 2 and fused.ntt_form
+    got = fused.download()
+    for i in range(n):
+        want = env.orc.rescale(L, 2, env.orc.relinearize(L, ct3[i].reshape(-1), env.relin))
+        eq(got[i], want, f"fused relinearize+rescale L={L} ct {i}")
+    two = env.ctx.rescale_to_next(env.ctx.relinearize(b))
+    eq(two.download(), got, "fused vs two calls")
+    assert abs(fused.scale - two.scale) <= 1e-9 * two.scale
+    env.ctx.relinearize_rescale(b, out=b)   # in place
+    eq(b.download(), got, "fused in place")
+
+
 def case_bfv_multiply(env, n0=2, n1=2):
     """K5: BFV (BEHZ) multiply over the result grid"""
     a, b = env.rand_ct(n0), env.rand_ct(n1)

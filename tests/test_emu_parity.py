@@ -67,6 +67,11 @@ def test_mul_relin_rescale(ckks):
     parity.case_mul_relin_rescale(ckks)
 
 
+def test_relin_rescale_fused(ckks):
+    for L in sorted({ckks.Ltop, max(2, ckks.Ltop - 1), 2}, reverse=True):
+        parity.case_relin_rescale_fused(ckks, L=L)
+
+
 def test_errors(ckks):
     parity.case_errors(ckks)
 
@@ -103,6 +108,7 @@ def test_split_limb(emu_lib):
         parity.case_ntt(env, n=1)
         parity.case_relinearize(env, n=1)
         parity.case_rescale(env, n=1, sizes=(2,))
+        parity.case_relin_rescale_fused(env, n=1)
         env.close()
 
 

@@ -79,6 +79,11 @@ def test_mul_relin_rescale(ckks):
     parity.case_mul_relin_rescale(ckks)
 
 
+def test_relin_rescale_fused(ckks):
+    for L in sorted({ckks.Ltop, max(2, ckks.Ltop - 1), 2}, reverse=True):
+        parity.case_relin_rescale_fused(ckks, L=L)
+
+
 def test_errors(ckks):
     parity.case_errors(ckks)
 

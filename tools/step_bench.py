@@ -48,6 +48,9 @@ if wl in ("dot", "rot"):
 def step():
     if wl == "mrr":
         ctx.multiply(A, B, out=R)
+        ctx.relinearize_rescale(R, out=R)
+    elif wl == "mrr2":   # the two separate calls
+        ctx.multiply(A, B, out=R)
         ctx.relinearize(R, out=R)
         ctx.rescale_to_next(R, out=R)
     elif wl == "dot":
