@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
                 x[reg] = v.x;
                 x[reg + 1] = v.y;
             });
+            __syncthreads();   // the transform buffer may still be read by the previous digit's transform
             co_to_contig(x, sm, tid);
         } else {
             const u64 *tp = A.tcoef + (size_t)b * A.tcoef_stride + (size_t)J * N;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
                 load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m, PreReduce{ m });
             else
                 load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m, PreNone());
-            ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
+            ntt_fwd_regs_split<LOGN, true>(x, sm, tw, m, tid, c, r, t0);
         }
         const bool fold = ((J + 1) % (int)m.acc_period) == 0;
 #pragma unroll
@@ -382,7 +383,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
 #pragma unroll
             for (int p = 0; p < 8; p++) st2(acc_sm[k] + (p * TH + tid) * 2, a[p].x, a[p].y);
         }
-        __syncthreads();   // the transform buffer is reused by the next digit
+        // no barrier here: the accumulator slots are thread-private, and the transform buffer is protected by the
+        // barrier in front of its next first store (REUSE)
     }
     if (c == 0 && I == L) {
         const ulonglong2 *itw = T.itw + (size_t)ki * T.N;
@@ -396,13 +398,13 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
                 x[reg] = reduce_full(a.x, m);
                 x[reg + 1] = reduce_full(a.y, m);
             });
-            ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0, tl);
+            ntt_inv_regs_split<LOGN, true, true>(x, sm, itw, m, tid, 0, 0, tl);
             u64 *out = A.rp + ((size_t)b * 2 + k) * N;
             for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, INV_ADDHALF), inv_finish(x[reg + 1], m, INV_ADDHALF)); });
-            __syncthreads();
         }
         return;
     }
+    __syncthreads();   // the epilogue stages through the transform buffer
 #pragma unroll 1
     for (int k = 0; k < 2; k++) {
         u64 *o = A.acc + (((size_t)b * 2 + k) * (L + 1) + I) * N + off;

@@ -273,8 +273,11 @@ __device__ __forceinline__ void bfly_inv(u64 (&x)[16], TwRegs<LOGN, P> &t, const
 // < 2q (+2q per split pre-stage); t = the pass-0 twiddles (load_tw_early<LOGN,0,false>, issued by the caller next
 // to its data loads).  Out: x in the contiguous layout (local coefficient 16*tid + j in x[j]), lazy
 // (any value < 2^64 congruent to the result: finish with reduce_full).
-// Uses sm (2^LOGN words).  Caller must __syncthreads() before reusing sm for another transform.
-template <int LOGN, int P = 0>
+// Uses sm (2^LOGN words).  A CTA that runs several transforms through the same buffer passes REUSE = true: the
+// CTA-wide barrier that protects the buffer then sits right before the first store into it -- after the global loads
+// and the first pass of butterflies -- so warps leave the previous transform's elementwise tail (and enter their loads)
+// at their own pace instead of in lockstep.
+template <int LOGN, bool REUSE = false, int P = 0>
 __device__ __forceinline__ void ntt_fwd_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ tw, const Mod &m, int tid, int c, int r,
                                                    TwRegs<LOGN, P> &t)
 {
@@ -282,17 +285,18 @@ __device__ __forceinline__ void ntt_fwd_regs_split(u64 (&x)[16], u64 *sm, const 
     if constexpr (P + 1 < Sched<LOGN>::NP) {
         TwRegs<LOGN, P + 1> tn;
         load_tw_early<LOGN, P + 1, false>(tn, tw, tid, (1 << c) + r);
+        if constexpr (REUSE && P == 0) __syncthreads();
         smem_xfer<LOGN, P, true>(x, sm, tid);
         xchg_sync<LOGN, P>(tid);
         smem_xfer<LOGN, P + 1, false>(x, sm, tid);
-        ntt_fwd_regs_split<LOGN, P + 1>(x, sm, tw, m, tid, c, r, tn);
+        ntt_fwd_regs_split<LOGN, REUSE, P + 1>(x, sm, tw, m, tid, c, r, tn);
     }
 }
 
 // Inverse transform of local chunk r.  In: x in the contiguous layout, canonical values (< q);
 // t = twiddles of the last pass (load_tw_early<LOGN,NP-1,true> on the inverse table).
 // Out: x in pass-0 layout; FINAL (unsplit limb): multiplied by N^{-1}, in [0,2q); otherwise lazy.
-template <int LOGN, bool FINAL, int P = Sched<LOGN>::NP - 1>
+template <int LOGN, bool FINAL, bool REUSE = false, int P = Sched<LOGN>::NP - 1>
 __device__ __forceinline__ void ntt_inv_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ itw, const Mod &m, int tid, int c, int r,
                                                    TwRegs<LOGN, P> &t)
 {
@@ -302,10 +306,11 @@ __device__ __forceinline__ void ntt_inv_regs_split(u64 (&x)[16], u64 *sm, const 
     if constexpr (P > 0) {
         TwRegs<LOGN, P - 1> tn;
         load_tw_early<LOGN, P - 1, true>(tn, itw, tid, (1 << c) + r);
+        if constexpr (REUSE && P == Sched<LOGN>::NP - 1) __syncthreads();
         smem_xfer<LOGN, P, true>(x, sm, tid);
         xchg_sync<LOGN, P - 1>(tid);
         smem_xfer<LOGN, P - 1, false>(x, sm, tid);
-        ntt_inv_regs_split<LOGN, FINAL, P - 1>(x, sm, itw, m, tid, c, r, tn);
+        ntt_inv_regs_split<LOGN, FINAL, REUSE, P - 1>(x, sm, itw, m, tid, c, r, tn);
     }
 }
 
