@@ -152,6 +152,9 @@ def test_full_batch(gpu_lib):
     x, y = env.rand_ct(n), env.rand_ct(n)
     X, Y = env.batch(x), env.batch(y)
     parity.eq(env.ctx.multiply(X, Y).download(), env.ctx.multiply(Y, X).download(), "multiply commutes")
+    P3 = env.ctx.multiply(X, Y)
+    parity.eq(env.ctx.relinearize_rescale(P3).download(), env.ctx.rescale_to_next(env.ctx.relinearize(P3)).download(),
+              "fused relinearize+rescale == the two calls over 1000 ciphertexts")
     parity.eq(env.ctx.sub(env.ctx.add(X, Y), Y).download(), x, "(x + y) - y = x")
     C = env.ctx.batch(x, ntt_form=False)
     parity.eq(env.ctx.ntt_inverse(env.ctx.ntt_forward(C)).download(), x, "inverse(forward) over 1000 ciphertexts")
