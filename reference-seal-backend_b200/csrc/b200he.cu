@@ -24,6 +24,25 @@
 
 #ifndef B200HE_EMU
 #define B200HE_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// launch with `cluster` consecutive CTAs per thread-block cluster (a limb split over 2^c CTAs, kernels.cuh)
+template <class... KArgs, class... Args>
+static inline void launch_cluster(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, unsigned cluster, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster > 1 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through cudaGetLastError() at the call site
+}
+#define B200HE_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) launch_cluster(kernel, (grid), (block), (smem), (stream), (cluster), __VA_ARGS__)
 #endif
 
 using namespace b200he;
@@ -162,6 +181,13 @@ static inline void prof_post(b200he_ctx *c)
         B200HE_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);     \
         prof_post(ctx);                                                           \
     } while (0)
+// NTT-bearing kernels: one cluster of 2^c CTAs per limb
+#define LAUNCHC(ctx, cls, kernel, grid, block, smem, ...)                                                        \
+    do {                                                                                                         \
+        prof_pre(ctx, cls);                                                                                      \
+        B200HE_LAUNCH_CLUSTER(kernel, grid, block, smem, (ctx)->stream, 1u << (ctx)->c, __VA_ARGS__);            \
+        prof_post(ctx);                                                                                          \
+    } while (0)
 #define LAUNCH_CHECK() CK(cudaGetLastError())
 
 // dispatch on the CTA-local transform size
@@ -171,6 +197,17 @@ static inline void prof_post(b200he_ctx *c)
     case 11: { constexpr int LG = 11; STMT; } break;              \
     case 12: { constexpr int LG = 12; STMT; } break;              \
     default: { constexpr int LG = 13; STMT; } break;              \
+    }
+// dispatch on the CTA-local transform size LG and the cluster exponent CC (limbs larger than 8192 coefficients are
+// split over 2 or 4 CTAs of 8192: CC > 0 only with LG = 13)
+#define KERNEL_DISPATCH(ctx, STMT)                                                      \
+    switch ((ctx)->lognl * 4 + (ctx)->c) {                                              \
+    case 40: { constexpr int LG = 10, CC = 0; STMT; } break;                            \
+    case 44: { constexpr int LG = 11, CC = 0; STMT; } break;                            \
+    case 48: { constexpr int LG = 12, CC = 0; STMT; } break;                            \
+    case 52: { constexpr int LG = 13, CC = 0; STMT; } break;                            \
+    case 53: { constexpr int LG = 13, CC = 1; STMT; } break;                            \
+    default: { constexpr int LG = 13, CC = 2; STMT; } break;                            \
     }
 
 static inline unsigned blocks_for(size_t threads, unsigned block = 256) { return (unsigned)((threads + block - 1) / block); }
@@ -276,14 +313,14 @@ static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std
     return 0;
 }
 
-template <int LG> static int set_smem_attrs()
+template <int LG, int CC> static int set_smem_attrs()
 {
 #ifndef B200HE_EMU
     const int bytes = NttCfg<LG>::SMEM_BYTES;
-    CK(cudaFuncSetAttribute(k_ntt_fwd<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_ntt_inv<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_ks_inner<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_moddown<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_ntt_fwd<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_ntt_inv<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 #endif
     return 0;
 }
@@ -325,7 +362,7 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
     c->lognl = logn > 13 ? 13 : logn;
     if (const char *e = getenv("B200HE_LOGNL")) {   // tuning knob: CTA-local transform size (limb split 2^(logn-lognl) ways, <= 4)
         const int v = atoi(e);
-        if (v >= 10 && v <= 13 && v <= logn && logn - v <= 2) c->lognl = v;
+        if (v >= 10 && v <= 13 && v == logn) c->lognl = v;   // limbs are split only into chunks of 8192
     }
     c->c = logn - c->lognl;
     c->t = plain_modulus;
@@ -337,8 +374,11 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
     c->own_stream = true;
 #endif
     int rc = 0;
-    NTT_DISPATCH(c, rc = set_smem_attrs<LG>());
+    KERNEL_DISPATCH(c, (rc = set_smem_attrs<LG, CC>()));
     if (rc) { delete c; return rc; }
+    // the tables were uploaded with synchronous copies from pageable memory (NULL stream): make sure they have landed
+    // before the first kernel on the context's non-blocking stream can run
+    if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return fail("ctx_create: device synchronisation failed"); }
     *out = c;
     return 0;
 }
@@ -450,7 +490,11 @@ static int galois_table(b200he_ctx *c, u32 elt, const u32 **out)
         }
         u32 *d = nullptr;
         CK(cudaMalloc((void **)&d, N * sizeof(u32)));
-        CK(cudaMemcpy(d, tab.data(), N * sizeof(u32), cudaMemcpyHostToDevice));
+        // on the context's stream: a plain cudaMemcpy from pageable memory may return before its DMA (ordered on the
+        // NULL stream, which this non-blocking stream does not wait for) has landed, and the permutation kernel would
+        // read a half-written table the first time an element is used
+        CK(cudaMemcpyAsync(d, tab.data(), N * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
         it = c->galtab.emplace(elt, d).first;
     }
     *out = it->second;
@@ -592,8 +636,8 @@ static bool same_scale(double a, double b) { return fabs(a - b) <= 1e-9 * fmax(f
 static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base)
 {
     if (!nlimbs) return 0;
-    NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_NTT_FWD, k_ntt_fwd<LG>, (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                           c->T, src, dst, src_outer, dst_outer, L, mod_base, c->c));
+    KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_FWD, (k_ntt_fwd<LG, CC>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
+                               c->T, src, dst, src_outer, dst_outer, L, mod_base));
     LAUNCH_CHECK();
     return 0;
 }
@@ -603,14 +647,9 @@ static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_
     if (!nlimbs) return 0;
     InvFuse F{};
     if (fuse) F = *fuse;
-    NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_NTT_INV, k_ntt_inv<LG>, (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                           c->T, src, dst, src_outer, dst_outer, L, mod_base, c->c, mode, F));
+    KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
+                               c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
     LAUNCH_CHECK();
-    if (c->c > 0) {
-        const size_t threads = nlimbs * ((size_t)c->N >> c->c) / 2;
-        LAUNCH(c, B200HE_KERN_NTT_INV_TAIL, k_ntt_inv_tail, blocks_for(threads), 256, 0, c->T, dst, dst_outer, nlimbs, L, mod_base, c->c, mode, F);
-        LAUNCH_CHECK();
-    }
     return 0;
 }
 
@@ -840,14 +879,10 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
             A.tcoef = tg; A.tcoef_stride = t_stride; A.target = nullptr; A.target_stride = 0;
         }
         A.key = key; A.acc = acc; A.rp = rp; A.L = L; A.K = (int)K; A.B = (int)nb;
-        NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_KS_INNER, k_ks_inner<LG>, (unsigned)((nb * (L + 1)) << c->c), NttCfg<LG>::THREADS,
-                               KsCfg<LG>::SMEM_BYTES, c->T, A, c->c));
+        // (the rounded special-prime limb comes out of k_ks_inner in coefficient form: rp)
+        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_KS_INNER, (k_ks_inner<LG, CC>), (unsigned)((nb * (L + 1)) << c->c), NttCfg<LG>::THREADS,
+                                   KsCfg<LG>::SMEM_BYTES, c->T, A));
         if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: k_ks_inner launch failed"); break; }
-        // rounded special-prime limb in coefficient form: fused into k_ks_inner for unsplit limbs
-        if (c->c > 0) {
-            rc = ntt_inv(c, acc + (size_t)L * N, rp, nb * 2, (size_t)(L + 1) * N, N, 1, (int)K - 1, INV_ADDHALF);
-            if (rc) break;
-        }
         ModDownArgs D{};
         D.rp = rp; D.base = acc; D.base_ct_stride = w_acc; D.base_poly_stride = (size_t)(L + 1) * N;
         D.addend[0] = add0 ? add0 + b0 * add_stride : nullptr;
@@ -865,11 +900,11 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
             rc = ntt_inv(c, acc + (size_t)(L - 1) * N, rp2, nb * 2, (size_t)(L + 1) * N, N, 1, L - 1, INV_ADDHALF, &F);
             if (rc) break;
             D.rp2 = rp2; D.x2 = L - 1; D.nJ = L - 1; D.out_poly_stride = (size_t)(L - 1) * N;
-            NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown<LG>, (unsigned)((nb * 2 * (L - 1)) << c->c), NttCfg<LG>::THREADS,
-                                   NttCfg<LG>::SMEM_BYTES, c->T, D, c->c));
+            KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * 2 * (L - 1)) << c->c), NttCfg<LG>::THREADS,
+                                   NttCfg<LG>::SMEM_BYTES, c->T, D));
         } else if (ckks) {
-            NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown<LG>, (unsigned)((nb * 2 * L) << c->c), NttCfg<LG>::THREADS,
-                                   NttCfg<LG>::SMEM_BYTES, c->T, D, c->c));
+            KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * 2 * L) << c->c), NttCfg<LG>::THREADS,
+                                   NttCfg<LG>::SMEM_BYTES, c->T, D));
         } else {
             // BFV: accumulators back to coefficient form (in place, unsplit per-limb strides), then elementwise mod-down
             rc = ntt_inv(c, acc, acc, nb * 2 * L, (size_t)(L + 1) * N, (size_t)(L + 1) * N, L, 0, INV_PLAIN);
@@ -1162,8 +1197,8 @@ extern "C" int b200he_rescale_to_next(b200he_ctx *c, const b200he_batch *in, b20
             rc = ntt_inv(c, src + (size_t)(L - 1) * N, rp, nb * P, (size_t)L * N, N, 1, L - 1, INV_ADDHALF);
             if (rc) break;
             D.rp = rp;
-            NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_MODDOWN, k_moddown<LG>, (unsigned)((nb * P * (L - 1)) << c->c), NttCfg<LG>::THREADS,
-                                   NttCfg<LG>::SMEM_BYTES, c->T, D, c->c));
+            KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * P * (L - 1)) << c->c), NttCfg<LG>::THREADS,
+                                   NttCfg<LG>::SMEM_BYTES, c->T, D));
         } else {
             // coefficient form: rp = last + q_last/2 mod q_last, elementwise
             D.rp = nullptr; D.rp_raw = src + (size_t)(L - 1) * N; D.rp_raw_stride = (size_t)L * N;

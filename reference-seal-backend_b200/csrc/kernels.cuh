@@ -19,6 +19,9 @@
 // tail kernel.
 #pragma once
 #include "ntt_core.cuh"
+#ifndef B200HE_EMU
+#include <cooperative_groups.h>
+#endif
 
 namespace b200he {
 
@@ -80,45 +83,170 @@ __device__ __forceinline__ void ct_lazy(u64 &a, u64 &b, ulonglong2 w, const Mod 
     a = a + v;
 }
 
-// Load the pass-0 register layout of local chunk r of a limb split 2^c ways, computing the
-// first c global stages on the fly.  src points at the limb (N_glob coefficients).
-// pre() must return values < 2q; the result is < (2 + 2c) q.
-template <int LOGN, class Pre>
-__device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restrict__ src, int c, int r, int tid,
-                                               const ulonglong2 *__restrict__ tw, const Mod &m, Pre pre)
+// ---- thread-block clusters: a limb of N = 2^c * NL coefficients belongs to a cluster of 2^c CTAs ----
+// CTA r of the cluster owns chunk r (coefficients [r NL, (r+1) NL)) in its registers / shared memory.  The c
+// transform stages that span chunks (the first c Cooley-Tukey stages, the last c Gentleman-Sande stages) pair the
+// SAME offset e of different chunks, so they run as one radix-2^c butterfly per offset on values exchanged through
+// distributed shared memory: every thread owns 16 >> c of its 16 offsets (register pairs [own r, own (r+1))), pulls
+// the other chunks' values at those offsets from the peers' transform buffers, computes all 2^c outputs once, keeps
+// its own and pushes the others back into the slots it just read.  No butterfly is computed twice and a limb
+// crosses HBM exactly once per direction for every N (the earlier design recomputed the cross stages per CTA from
+// global memory and finished split inverses in a second kernel).
+#ifdef B200HE_EMU
+__device__ __forceinline__ void cluster_sync() { emu::cluster_sync(); }
+__device__ __forceinline__ u64 *cluster_peer(u64 *sm, int rank)
 {
-    constexpr int NL = 1 << LOGN;
-    if (c == 0) {
-        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            const ulonglong2 v = pre.pair(ldg2(src + e), e);
+    return reinterpret_cast<u64 *>(emu::cluster_smem((unsigned)rank) + (reinterpret_cast<unsigned char *>(sm) - emu::block_smem()));
+}
+#else
+__device__ __forceinline__ void cluster_sync() { cooperative_groups::this_cluster().sync(); }
+__device__ __forceinline__ u64 *cluster_peer(u64 *sm, int rank) { return cooperative_groups::this_cluster().map_shared_rank(sm, (unsigned)rank); }
+#endif
+
+// publish the register pairs owned by other CTAs / fetch them back after the owners have pushed the results
+template <int LOGN> __device__ __forceinline__ void cross_publish(const u64 (&x)[16], u64 *sm, int c, int r, int tid)
+{
+    const int own = 16 >> c;
+    for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+        if (reg / own != r) st2(sm + swz(e), x[reg], x[reg + 1]);
+    });
+}
+template <int LOGN> __device__ __forceinline__ void cross_collect(u64 (&x)[16], const u64 *sm, int c, int r, int tid)
+{
+    const int own = 16 >> c;
+    for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+        if (reg / own != r) {
+            const ulonglong2 v = ld2(sm + swz(e));
             x[reg] = v.x;
             x[reg + 1] = v.y;
-        });
-    } else if (c == 1) {
+        }
+    });
+}
+
+// First c Cooley-Tukey stages across the chunks of a cluster.  In: x = pass-0 layout of chunk r, values < 2q.
+// Out: the same registers after global stages 0..c-1, values < (2 + 2c) q.  Twiddles: stage 0 tw[1]; stage 1 tw[2]
+// (chunks 0,1) and tw[3] (chunks 2,3).
+template <int LOGN>
+__device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, int tid, const ulonglong2 *__restrict__ tw, const Mod &m)
+{
+    const int own = 16 >> c;
+    cross_publish<LOGN>(x, sm, c, r, tid);
+    cluster_sync();
+    if (c == 1) {
+        u64 *peer = cluster_peer(sm, r ^ 1);
         const ulonglong2 w = ld_tw(tw + 1);
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            const ulonglong2 a = pre.pair(ldg2(src + e), e), b = pre.pair(ldg2(src + e + NL), e + NL);
-            u64 a0 = a.x, a1 = a.y, b0 = b.x, b1 = b.y;
+            if (reg / own != r) return;
+            const ulonglong2 pv = ld2(peer + swz(e));
+            u64 a0 = r ? pv.x : x[reg], a1 = r ? pv.y : x[reg + 1];   // chunk 0
+            u64 b0 = r ? x[reg] : pv.x, b1 = r ? x[reg + 1] : pv.y;   // chunk 1
             ct_lazy(a0, b0, w, m);
             ct_lazy(a1, b1, w, m);
             x[reg] = r ? b0 : a0;
             x[reg + 1] = r ? b1 : a1;
+            st2(peer + swz(e), r ? a0 : b0, r ? a1 : b1);
         });
     } else {
-        const ulonglong2 w1 = ld_tw(tw + 1), w2 = ld_tw(tw + 2 + (r >> 1));
+        u64 *peer[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) peer[q] = cluster_peer(sm, q);
+        const ulonglong2 w1 = ld_tw(tw + 1), w2 = ld_tw(tw + 2), w3 = ld_tw(tw + 3);
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            const ulonglong2 v0 = pre.pair(ldg2(src + e), e), v1 = pre.pair(ldg2(src + e + NL), e + NL),
-                             v2 = pre.pair(ldg2(src + e + 2 * NL), e + 2 * NL), v3 = pre.pair(ldg2(src + e + 3 * NL), e + 3 * NL);
+            if (reg / own != r) return;
+            ulonglong2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = (q == r) ? make_ulonglong2(x[reg], x[reg + 1]) : ld2(peer[q] + swz(e));
+            u64 o[4][2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                u64 a0 = h ? v0.y : v0.x, a1 = h ? v1.y : v1.x, a2 = h ? v2.y : v2.x, a3 = h ? v3.y : v3.x;
+                u64 a0 = h ? v[0].y : v[0].x, a1 = h ? v[1].y : v[1].x, a2 = h ? v[2].y : v[2].x, a3 = h ? v[3].y : v[3].x;
                 ct_lazy(a0, a2, w1, m);
                 ct_lazy(a1, a3, w1, m);
-                u64 u = (r >> 1) ? a2 : a0, v = (r >> 1) ? a3 : a1;
-                ct_lazy(u, v, w2, m);
-                x[reg + h] = (r & 1) ? v : u;
+                ct_lazy(a0, a1, w2, m);
+                ct_lazy(a2, a3, w3, m);
+                o[0][h] = a0; o[1][h] = a1; o[2][h] = a2; o[3][h] = a3;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (q == r) { x[reg] = o[q][0]; x[reg + 1] = o[q][1]; }
+                else st2(peer[q] + swz(e), o[q][0], o[q][1]);
             }
         });
+    }
+    cluster_sync();
+    cross_collect<LOGN>(x, sm, c, r, tid);
+}
+
+// Last c Gentleman-Sande stages across the chunks of a cluster, with N^{-1} folded into the final one.
+// In: x = pass-0 layout of chunk r after the local stages, reduced to [0, 2q).  Out: finished values in [0, 2q).
+template <int LOGN>
+__device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, int tid, const ulonglong2 *__restrict__ itw, const Mod &m)
+{
+    const int own = 16 >> c;
+    cross_publish<LOGN>(x, sm, c, r, tid);
+    cluster_sync();
+    const ulonglong2 wn = ld_tw(itw);
+    if (c == 1) {
+        u64 *peer = cluster_peer(sm, r ^ 1);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            if (reg / own != r) return;
+            const ulonglong2 pv = ld2(peer + swz(e));
+            const u64 a0 = r ? pv.x : x[reg], a1 = r ? pv.y : x[reg + 1], b0 = r ? x[reg] : pv.x, b1 = r ? x[reg + 1] : pv.y;
+            const u64 s0 = shoup_lazy(a0 + b0, m.ninv, m.ninv_s, m.q), s1 = shoup_lazy(a1 + b1, m.ninv, m.ninv_s, m.q);
+            const u64 d0 = shoup_lazy(a0 - b0 + m.two_q, wn.x, wn.y, m.q), d1 = shoup_lazy(a1 - b1 + m.two_q, wn.x, wn.y, m.q);
+            x[reg] = r ? d0 : s0;
+            x[reg + 1] = r ? d1 : s1;
+            st2(peer + swz(e), r ? s0 : d0, r ? s1 : d1);
+        });
+    } else {
+        u64 *peer[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) peer[q] = cluster_peer(sm, q);
+        const ulonglong2 w2 = ld_tw(itw + 2), w3 = ld_tw(itw + 3);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            if (reg / own != r) return;
+            ulonglong2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = (q == r) ? make_ulonglong2(x[reg], x[reg + 1]) : ld2(peer[q] + swz(e));
+            u64 o[4][2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                u64 a0 = h ? v[0].y : v[0].x, a1 = h ? v[1].y : v[1].x, a2 = h ? v[2].y : v[2].x, a3 = h ? v[3].y : v[3].x;
+                gs_bfly(a0, a1, w2.x, w2.y, m.q, m.two_q);
+                gs_bfly(a2, a3, w3.x, w3.y, m.q, m.two_q);
+                o[0][h] = shoup_lazy(a0 + a2, m.ninv, m.ninv_s, m.q);
+                o[2][h] = shoup_lazy(a0 - a2 + m.two_q, wn.x, wn.y, m.q);
+                o[1][h] = shoup_lazy(a1 + a3, m.ninv, m.ninv_s, m.q);
+                o[3][h] = shoup_lazy(a1 - a3 + m.two_q, wn.x, wn.y, m.q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (q == r) { x[reg] = o[q][0]; x[reg + 1] = o[q][1]; }
+                else st2(peer[q] + swz(e), o[q][0], o[q][1]);
+            }
+        });
+    }
+    cluster_sync();
+    cross_collect<LOGN>(x, sm, c, r, tid);
+}
+
+// Load the pass-0 register layout of chunk r of a limb (src points at the limb, N = NL << c coefficients), apply the
+// input transform, and run the c cross-chunk stages.  pre.pair() must return values < 2q; the result is < (2 + 2c) q.
+// REUSE: the CTA has used the transform buffer before (see ntt_fwd_regs_split).
+template <int LOGN, bool REUSE = false, class Pre>
+__device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restrict__ src, int c, int r, int tid,
+                                               const ulonglong2 *__restrict__ tw, const Mod &m, Pre pre, u64 *sm)
+{
+    constexpr int NL = 1 << LOGN;
+    const size_t off = (size_t)r * NL;
+    for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+        const ulonglong2 v = pre.pair(ldg2(src + off + e), off + e);
+        x[reg] = v.x;
+        x[reg + 1] = v.y;
+    });
+    if (c > 0) {
+        if (REUSE) __syncthreads();
+        cross_fwd<LOGN>(x, sm, c, r, tid, tw, m);
     }
 }
 
@@ -126,10 +254,13 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
 // dst[w] = NTT(src[w]) for w < nlimbs; modulus id = mod_base + (w % L).  grid = nlimbs << c.
 // Limb w lives at base + (w / L) * outer + (w % L) * N  (outer = L*N for a contiguous batch; a larger
 // outer stride addresses one limb per polynomial, e.g. the special-prime limb of the key-switch accumulator).
-template <int LOGN>
+// C = log2 of the cluster size (CTAs per limb), a compile-time constant so that the unsplit case carries none of
+// the cluster code.
+template <int LOGN, int C>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
-                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base, int c)
+                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base)
 {
+    constexpr int c = C;
     constexpr int NL = 1 << LOGN;
     u64 *sm = dyn_smem();
     const int tid = threadIdx.x;
@@ -140,7 +271,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd(Tables T, con
     u64 x[16];
     TwRegs<LOGN, 0> t0;
     load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
-    load_fwd_split<LOGN>(x, src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N, c, r, tid, tw, m, PreNone());
+    load_fwd_split<LOGN>(x, src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N, c, r, tid, tw, m, PreNone(), sm);
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     canon_all(x, m);
@@ -173,11 +304,12 @@ __device__ __forceinline__ u64 inv_post(u64 v /* finished, canonical */, u64 sub
 {
     return sub_mod(v, shoup(reduce64(subv, m) + fix, s.x, s.y, m.q), m.q);
 }
-// c == 0: dst = iNTT(src) (finished).  c > 0: dst = partial (local stages only, values in [0,2q)).
-template <int LOGN>
+// dst = iNTT(src), finished (c > 0: the cluster's CTAs exchange the cross-chunk stages through DSMEM).
+template <int LOGN, int C>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
-                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base, int c, int mode, InvFuse F)
+                                                                   size_t src_outer, size_t dst_outer, int L, int mod_base, int mode, InvFuse F)
 {
+    constexpr int c = C;
     constexpr int NL = 1 << LOGN;
     u64 *sm = dyn_smem();
     const int tid = threadIdx.x;
@@ -209,82 +341,25 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     }
     co_to_contig(x, sm, tid);
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
-    if (c == 0) {
+    if (c == 0)
         ntt_inv_regs_split<LOGN, true>(x, sm, itw, m, tid, 0, 0, tl);
-        if (F.add) {
-            const u64 *sb = F.sub + (size_t)w * T.N;
-            for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-                const ulonglong2 u = ldg2(sb + e);
-                const u64 v0 = inv_post(csub(x[reg], m.q), u.x, m, fs, ffix), v1 = inv_post(csub(x[reg + 1], m.q), u.y, m, fs, ffix);
-                st2(out + e, mode == INV_ADDHALF ? csub(v0 + (m.q >> 1), m.q) : v0, mode == INV_ADDHALF ? csub(v1 + (m.q >> 1), m.q) : v1);
-            });
-            return;
-        }
-        for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, mode), inv_finish(x[reg + 1], m, mode)); });
-    } else {
+    else {
         ntt_inv_regs_split<LOGN, false>(x, sm, itw, m, tid, c, r, tl);
         reduce_all(x, m);
-        for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
+        cross_inv<LOGN>(x, sm, c, r, tid, itw, m);
     }
-}
-// Tail of a split inverse: the last c Gentleman-Sande stages across the 2^c chunks, N^{-1}, finish.
-// One thread per coefficient pair of a chunk; in place.  grid covers nlimbs * (N >> c) / 2 threads.
-__global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict__ data, size_t outer, size_t nlimbs, int L, int mod_base, int c, int mode,
-                                                      InvFuse F)
-{
-    const size_t chunk = (size_t)T.N >> c, per_limb = chunk / 2;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nlimbs * per_limb) return;
-    const size_t w = gid / per_limb, e = (gid % per_limb) * 2;
-    const int mid = mod_base + (int)(w % L);
-    const Mod m = T.mods[mid];
-    const ulonglong2 *itw = T.itw + (size_t)mid * T.N;
-    u64 *p = data + (w / L) * outer + (w % L) * T.N + e;
-    const ulonglong2 wn = ld_tw(itw);
-    // finish of output pair k (limb index e + k * chunk): canonical value, fused mod-down correction, rounding
-    ulonglong2 fs = make_ulonglong2(0, 0);
-    u64 ffix = 0;
+    // x: finished values in [0, 2q), pass-0 layout of chunk r
     if (F.add) {
-        fs = T.qinv[(size_t)F.x * T.M + mid];
-        ffix = m.q - T.halfmod[(size_t)F.x * T.M + mid];
+        const u64 *sb = F.sub + (size_t)w * T.N + (size_t)r * NL;
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            const ulonglong2 u = ldg2(sb + e);
+            const u64 v0 = inv_post(csub(x[reg], m.q), u.x, m, fs, ffix), v1 = inv_post(csub(x[reg + 1], m.q), u.y, m, fs, ffix);
+            st2(out + e, mode == INV_ADDHALF ? csub(v0 + (m.q >> 1), m.q) : v0, mode == INV_ADDHALF ? csub(v1 + (m.q >> 1), m.q) : v1);
+        });
+        return;
     }
-    auto fin = [&](u64 lazy0, u64 lazy1, int k) {
-        if (!F.add) return make_ulonglong2(inv_finish(lazy0, m, mode), inv_finish(lazy1, m, mode));
-        const ulonglong2 u = ld2(F.sub + w * T.N + e + (size_t)k * chunk);
-        const u64 v0 = inv_post(csub(lazy0, m.q), u.x, m, fs, ffix), v1 = inv_post(csub(lazy1, m.q), u.y, m, fs, ffix);
-        return make_ulonglong2(mode == INV_ADDHALF ? csub(v0 + (m.q >> 1), m.q) : v0, mode == INV_ADDHALF ? csub(v1 + (m.q >> 1), m.q) : v1);
-    };
-    if (c == 1) {
-        ulonglong2 a = ld2(p), b = ld2(p + chunk);
-        u64 s0 = a.x + b.x, d0 = a.x - b.x + m.two_q, s1 = a.y + b.y, d1 = a.y - b.y + m.two_q;
-        const ulonglong2 o0 = fin(shoup_lazy(s0, m.ninv, m.ninv_s, m.q), shoup_lazy(s1, m.ninv, m.ninv_s, m.q), 0);
-        const ulonglong2 o1 = fin(shoup_lazy(d0, wn.x, wn.y, m.q), shoup_lazy(d1, wn.x, wn.y, m.q), 1);
-        st2(p, o0.x, o0.y);
-        st2(p + chunk, o1.x, o1.y);
-    } else {
-        ulonglong2 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = ld2(p + k * chunk);
-        const ulonglong2 w2 = ld_tw(itw + 2), w3 = ld_tw(itw + 3);
-        u64 o[4][2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            u64 a0 = h ? v[0].y : v[0].x, a1 = h ? v[1].y : v[1].x, a2 = h ? v[2].y : v[2].x, a3 = h ? v[3].y : v[3].x;
-            gs_bfly(a0, a1, w2.x, w2.y, m.q, m.two_q);
-            gs_bfly(a2, a3, w3.x, w3.y, m.q, m.two_q);
-            o[0][h] = shoup_lazy(a0 + a2, m.ninv, m.ninv_s, m.q);
-            o[2][h] = shoup_lazy(a0 - a2 + m.two_q, wn.x, wn.y, m.q);
-            o[1][h] = shoup_lazy(a1 + a3, m.ninv, m.ninv_s, m.q);
-            o[3][h] = shoup_lazy(a1 - a3 + m.two_q, wn.x, wn.y, m.q);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const ulonglong2 ov = fin(o[k][0], o[k][1], k);
-            st2(p + k * chunk, ov.x, ov.y);
-        }
-    }
+    for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, mode), inv_finish(x[reg + 1], m, mode)); });
 }
-
 // ------------------------------------------------------------------------------------ K6 step 2
 // acc[b][k][I] = sum_J NTT_{q_I}(t[b][J] mod q_I) (.) key[J][k][I]      (I == L  <->  special prime)
 // CKKS: the I == J term reuses the NTT-form target.  grid = B * (L+1) << c.
@@ -296,9 +371,9 @@ __global__ void __launch_bounds__(256) k_ntt_inv_tail(Tables T, u64 *__restrict_
 // transform output needs no reduction) -- and the accumulators stay lazy (Mod::acc_period).  The two
 // accumulator limbs live in shared memory between digits ([p][tid] pairs, conflict-free 128-bit
 // accesses) so the transform has the whole register file.
-// Unsplit limbs (c == 0): the CTA of the special prime finishes with the inverse transform and the
-// "+ q_sp/2" rounding of its two accumulators and writes them straight to rp (the input of
-// k_moddown); that limb never goes to HBM in NTT form.
+// The CTA (cluster) of the special prime finishes with the inverse transform and the "+ q_sp/2" rounding of
+// its two accumulators and writes them straight to rp (the input of k_moddown); that limb never goes to HBM
+// in NTT form.
 struct KsInnerArgs {
     const u64 *tcoef;      // target in coefficient form: tcoef + b*tcoef_stride + J*N
     size_t tcoef_stride;
@@ -306,15 +381,16 @@ struct KsInnerArgs {
     size_t target_stride;
     const u64 *key;        // [Ltop][2][K] limbs of 2N words: keys interleaved with their Shoup quotients (k_shoup_quotients)
     u64 *acc;              // [B][2][L+1][N]
-    u64 *rp;               // [B][2][N]: rounded special-prime limb in coefficient form (written when c == 0)
+    u64 *rp;               // [B][2][N]: rounded special-prime limb in coefficient form
     int L, K, B;           // B = ciphertexts in this launch
 };
 template <int LOGN> struct KsCfg {
     static constexpr int SMEM_BYTES = 3 * NttCfg<LOGN>::SMEM_BYTES;   // transform buffer + 2 accumulator limbs
 };
-template <int LOGN>
-__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T, KsInnerArgs A, int c)
+template <int LOGN, int C>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T, KsInnerArgs A)
 {
+    constexpr int c = C;
     constexpr int NL = 1 << LOGN, TH = NttCfg<LOGN>::THREADS;
     u64 *sm = dyn_smem();
     u64 *acc_sm[2] = { sm + NL, sm + 2 * NL };
@@ -349,9 +425,9 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
             TwRegs<LOGN, 0> t0;
             load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
             if (T.mods[J].q > m.q)
-                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m, PreReduce{ m });
+                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce{ m }, sm);
             else
-                load_fwd_split<LOGN>(x, tp, c, r, tid, tw, m, PreNone());
+                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
             ntt_fwd_regs_split<LOGN, true>(x, sm, tw, m, tid, c, r, t0);
         }
         const bool fold = ((J + 1) % (int)m.acc_period) == 0;
@@ -386,20 +462,26 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
         // no barrier here: the accumulator slots are thread-private, and the transform buffer is protected by the
         // barrier in front of its next first store (REUSE)
     }
-    if (c == 0 && I == L) {
+    if (I == L) {
         const ulonglong2 *itw = T.itw + (size_t)ki * T.N;
 #pragma unroll 1
         for (int k = 0; k < 2; k++) {
             u64 x[16];
             TwRegs<LOGN, Sched<LOGN>::NP - 1> tl;
-            load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, 1);
+            load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, (1 << c) + r);
             for_pairs_contig(tid, [&](int reg, int e) {
                 const ulonglong2 a = ld2(acc_sm[k] + ((reg >> 1) * TH + tid) * 2);
                 x[reg] = reduce_full(a.x, m);
                 x[reg + 1] = reduce_full(a.y, m);
             });
-            ntt_inv_regs_split<LOGN, true, true>(x, sm, itw, m, tid, 0, 0, tl);
-            u64 *out = A.rp + ((size_t)b * 2 + k) * N;
+            if (c == 0)
+                ntt_inv_regs_split<LOGN, true, true>(x, sm, itw, m, tid, 0, 0, tl);
+            else {
+                ntt_inv_regs_split<LOGN, false, true>(x, sm, itw, m, tid, c, r, tl);
+                reduce_all(x, m);
+                cross_inv<LOGN>(x, sm, c, r, tid, itw, m);
+            }
+            u64 *out = A.rp + ((size_t)b * 2 + k) * N + off;
             for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, INV_ADDHALF), inv_finish(x[reg + 1], m, INV_ADDHALF)); });
         }
         return;
@@ -472,9 +554,10 @@ struct ModDownArgs {
     const u64 *rp2;
     int x2;
 };
-template <int LOGN>
-__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, ModDownArgs A, int c)
+template <int LOGN, int C>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, ModDownArgs A)
 {
+    constexpr int c = C;
     constexpr int NL = 1 << LOGN;
     u64 *sm = dyn_smem();
     const int tid = threadIdx.x;
@@ -498,7 +581,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         const ulonglong2 ri = T.qinv[(size_t)A.x2 * T.M + j];
         const u64 fix2 = m.q - T.halfmod[(size_t)A.x2 * T.M + j];
         load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
-                             PreTwo{ m, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N });
+                             PreTwo{ m, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
         ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
         canon_all(x, m);
         contig_to_co(x, sm, tid);
@@ -510,7 +593,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         });
         return;
     }
-    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m, fix });
+    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m, fix }, sm);
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     canon_all(x, m);
     contig_to_co(x, sm, tid);

@@ -2,6 +2,7 @@
 #include "cuda_shim.h"
 
 #include <stdio.h>
+#include <sys/mman.h>
 
 emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
@@ -14,10 +15,12 @@ struct Fiber {
 };
 ucontext_t g_main;
 std::vector<Fiber> g_fibers;
-std::vector<unsigned char> g_stacks;
+unsigned char *g_stacks = nullptr;   // mmap'ed, untouched pages cost nothing
+size_t g_stacks_size = 0;
 std::vector<unsigned char> g_smem;
+size_t g_smem_stride = 0;
 const std::function<void()> *g_body = nullptr;
-unsigned g_cur = 0;
+unsigned g_cur = 0, g_block = 1;
 
 void trampoline()
 {
@@ -27,42 +30,57 @@ void trampoline()
 }
 }   // namespace
 
-unsigned char *block_smem() { return g_smem.data(); }
+unsigned char *block_smem() { return g_smem.data() + (size_t)(g_cur / g_block) * g_smem_stride; }
+unsigned char *cluster_smem(unsigned rank) { return g_smem.data() + (size_t)rank * g_smem_stride; }
+unsigned cluster_rank() { return g_cur / g_block; }
 
+// every barrier (block-wide, sub-block or cluster-wide) yields to the scheduler, which resumes a fiber only after
+// all fibers of the cluster have yielded: a superset of the synchronisation the kernels ask for
 void sync() { swapcontext(&g_fibers[g_cur].ctx, &g_main); }
+void cluster_sync() { sync(); }
 
-void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body)
+// the `cluster` consecutive blocks of a thread-block cluster run together (their fibers share one scheduler round)
+void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body, unsigned cluster)
 {
     g_body = &body;
     gridDim.x = grid;
     blockDim.x = block;
-    if (g_stacks.size() < (size_t)block * STACK) g_stacks.resize((size_t)block * STACK);
-    g_smem.assign(smem + 16, 0xA5);   // poison: kernels must not read uninitialised shared memory
-    g_fibers.resize(block);
-    for (unsigned b = 0; b < grid; b++) {
-        blockIdx.x = b;
-        for (unsigned t = 0; t < block; t++) {
+    g_block = block;
+    const unsigned nf = block * cluster;
+    if (g_stacks_size < (size_t)nf * STACK) {
+        if (g_stacks) munmap(g_stacks, g_stacks_size);
+        g_stacks_size = (size_t)nf * STACK;
+        g_stacks = (unsigned char *)mmap(nullptr, g_stacks_size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (g_stacks == MAP_FAILED) { perror("emu: mmap"); abort(); }
+    }
+    g_smem_stride = (smem + 16 + 127) / 128 * 128;
+    g_fibers.resize(nf);
+    if (grid % cluster) { fprintf(stderr, "emu: grid %u is not a multiple of the cluster size %u\n", grid, cluster); abort(); }
+    for (unsigned b0 = 0; b0 < grid; b0 += cluster) {
+        g_smem.assign(g_smem_stride * cluster, 0xA5);   // poison: kernels must not read uninitialised shared memory
+        for (unsigned t = 0; t < nf; t++) {
             Fiber &f = g_fibers[t];
             f.done = false;
             getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = g_stacks.data() + (size_t)t * STACK;
+            f.ctx.uc_stack.ss_sp = g_stacks + (size_t)t * STACK;
             f.ctx.uc_stack.ss_size = STACK;
             f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, trampoline, 0);
         }
         for (;;) {
             unsigned alive = 0, finished = 0;
-            for (unsigned t = 0; t < block; t++) {
+            for (unsigned t = 0; t < nf; t++) {
                 if (g_fibers[t].done) continue;
                 alive++;
                 g_cur = t;
-                threadIdx.x = t;
+                threadIdx.x = t % block;
+                blockIdx.x = b0 + t / block;
                 swapcontext(&g_main, &g_fibers[t].ctx);
                 if (g_fibers[t].done) finished++;
             }
             if (alive == 0) break;
             if (finished != 0 && finished != alive) {
-                fprintf(stderr, "emu: divergent barrier in block %u (%u of %u threads exited)\n", b, finished, alive);
+                fprintf(stderr, "emu: divergent barrier in cluster at block %u (%u of %u threads exited)\n", b0, finished, alive);
                 abort();
             }
         }

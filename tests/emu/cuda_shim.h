@@ -32,8 +32,11 @@ extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace emu {
 unsigned char *block_smem();
+unsigned char *cluster_smem(unsigned rank);   // shared memory of block `rank` of the running cluster (DSMEM)
+unsigned cluster_rank();
 void sync();
-void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body);
+void cluster_sync();
+void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body, unsigned cluster = 1);
 }
 #define __syncthreads() emu::sync()
 
@@ -65,3 +68,5 @@ static inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 
 #define B200HE_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::run_grid((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#define B200HE_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) \
+    emu::run_grid((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); }, (unsigned)(cluster))
