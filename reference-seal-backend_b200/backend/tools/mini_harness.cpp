@@ -6,7 +6,7 @@
 // the line the reference's CI greps ("[ Info    ] Failed: 0", R/.github/workflows/validate_testharness_output.sh:7).
 //
 //   mini_harness --backend_lib_path libhebench_seal_backend.so [--random_seed 1234] [--filter TEXT] [--list]
-//                [--samples A,B] [--batch N] [--iterations K] [--n N] [--dims R,C0,C1] [--poly N] [--csv FILE]
+//                [--samples A,B] [--batch N] [--iterations K] [--n N] [--dims R,C0,C1] [--poly N] [--depth D] [--csv FILE]
 #include <dlfcn.h>
 
 #include <chrono>
@@ -31,7 +31,7 @@ struct Options {
     std::string lib, filter, csv;
     unsigned seed = 1234;
     bool list = false;
-    uint64_t samples[2] = { 2, 3 }, batch = 8, iterations = 2, n = 0, dims[3] = { 0, 0, 0 }, poly = 0;
+    uint64_t samples[2] = { 2, 3 }, batch = 8, iterations = 2, n = 0, dims[3] = { 0, 0, 0 }, poly = 0, depth = 0;
 };
 
 static const char *workloadName(Workload w)
@@ -90,6 +90,7 @@ int main(int argc, char **argv)
         else if (a == "--n") o.n = strtoull(next().c_str(), nullptr, 10);
         else if (a == "--dims") sscanf(next().c_str(), "%lu,%lu,%lu", &o.dims[0], &o.dims[1], &o.dims[2]);
         else if (a == "--poly") o.poly = strtoull(next().c_str(), nullptr, 10);
+        else if (a == "--depth") o.depth = strtoull(next().c_str(), nullptr, 10);
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     if (o.lib.empty()) { fprintf(stderr, "usage: mini_harness --backend_lib_path <lib.so> [options]\n"); return 2; }
@@ -144,6 +145,7 @@ int main(int argc, char **argv)
         if (is_mat) { for (int k = 0; k < 3; ++k) if (o.dims[k]) wp[k].u_param = o.dims[k]; }
         else if (o.n) wp[0].u_param = o.n;
         if (o.poly) wp[is_mat ? 3 : 1].u_param = o.poly;
+        if (o.depth) wp[is_mat ? 4 : 2].u_param = o.depth;   // MultiplicativeDepth follows PolyModulusDegree
         const bool f64 = bd.data_type == Float64;
         // concrete sample counts
         uint64_t s0 = 1, s1 = 1, batch = 1;

@@ -46,27 +46,28 @@ __device__ __forceinline__ u64 *dyn_smem()
 
 // Input transforms fused into the first-pass load: pair(v, idx) maps the coefficient pair at limb index idx, idx+1.
 struct PreNone { __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return v; } };
+// (the functors carry q and floor(2^64/q) only: a by-value copy of the whole Mod lands in local memory)
+__device__ __forceinline__ u64 reduce64_qr(u64 x, u64 q, u64 r64) { return csub(x - mulhi64(x, r64) * q, q); }
 struct PreReduce {   // v mod q (lift of a digit into another modulus, SEAL modulo_poly_coeffs)
-    Mod m;
-    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64(v.x, m), reduce64(v.y, m)); }
+    u64 q, r64;
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64_qr(v.x, q, r64), reduce64_qr(v.y, q, r64)); }
 };
 struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_last/2 mod q))
-    Mod m;
-    u64 fix;
-    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64(v.x, m) + fix, reduce64(v.y, m) + fix); }
+    u64 q, r64, fix;
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64_qr(v.x, q, r64) + fix, reduce64_qr(v.y, q, r64) + fix); }
 };
 // Fused relinearize + rescale (k_moddown with two rounded limbs): the two mod-down corrections of output limb j,
 // NTT(u1) * s * r (key switch, s = q_sp^{-1}) and NTT(u2) * r (rescale, r = q_last^{-1}), are one transform of
 // (u1 * s + u2) * r because the transform is linear over Z_q.  Result in [0, 2q).
 struct PreTwo {
-    Mod m;
+    u64 q, r64;
     u64 fix1, fix2;
     ulonglong2 s, r;
     const u64 *rp2;
     __device__ __forceinline__ u64 one(u64 v1, u64 v2) const
     {
-        const u64 a = shoup_lazy(reduce64(v1, m) + fix1, s.x, s.y, m.q);
-        return shoup_lazy(a + reduce64(v2, m) + fix2, r.x, r.y, m.q);
+        const u64 a = shoup_lazy(reduce64_qr(v1, q, r64) + fix1, s.x, s.y, q);
+        return shoup_lazy(a + reduce64_qr(v2, q, r64) + fix2, r.x, r.y, q);
     }
     __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t idx) const
     {
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
             TwRegs<LOGN, 0> t0;
             load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
             if (T.mods[J].q > m.q)
-                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce{ m }, sm);
+                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce{ m.q, m.r64 }, sm);
             else
                 load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
             ntt_fwd_regs_split<LOGN, true>(x, sm, tw, m, tid, c, r, t0);
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         const ulonglong2 ri = T.qinv[(size_t)A.x2 * T.M + j];
         const u64 fix2 = m.q - T.halfmod[(size_t)A.x2 * T.M + j];
         load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
-                             PreTwo{ m, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
+                             PreTwo{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
         ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
         canon_all(x, m);
         contig_to_co(x, sm, tid);
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         });
         return;
     }
-    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m, fix }, sm);
+    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m.q, m.r64, fix }, sm);
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     canon_all(x, m);
     contig_to_co(x, sm, tid);

@@ -22,7 +22,8 @@ batch = int(sys.argv[5]) if len(sys.argv) > 5 else 1000
 iters = int(sys.argv[6]) if len(sys.argv) > 6 else 5
 
 host = Host(CKKS, N, depth, bits, bits)
-ctx = hb.Context(CKKS, N, host.moduli, host.psi, 0)
+lib = hb.load_library(os.environ["B200HE_LIB"]) if os.environ.get("B200HE_LIB") else None   # experiment builds
+ctx = hb.Context(CKKS, N, host.moduli, host.psi, 0, lib=lib)
 ctx.set_relin_key(host.relin_key())
 L = host.Ltop
 rng = np.random.default_rng(1)
