@@ -141,11 +141,7 @@ __device__ __forceinline__ void load_tw_range(TwRegs<LOGN, P> &t, const ulonglon
 #pragma unroll
     for (int u = U0; u < U1; u++)
 #pragma unroll
-#ifdef B200HE_EXP_TW
-        for (int blk = 0; blk < (1 << u); blk++) t.w[(1 << u) - 1 + blk] = ld_tw(tw + ((pre << (G::S + u)) + (hi << u) + blk) % 64);
-#else
         for (int blk = 0; blk < (1 << u); blk++) t.w[(1 << u) - 1 + blk] = ld_tw(tw + (pre << (G::S + u)) + (hi << u) + blk);
-#endif
 }
 template <int K> struct TwSplit {
     static constexpr int FWD_EARLY_END = K <= 3 ? K : 3;      // forward runs u = 0..K-1
