@@ -964,7 +964,10 @@ extern "C" int b200he_relinearize_rescale(b200he_ctx *c, const b200he_batch *in,
 }
 
 // ------------------------------------------------------------------------------------ Galois (K8)
-extern "C" int b200he_apply_galois(b200he_ctx *c, const b200he_batch *in, uint32_t elt, b200he_batch *out)
+// out = apply_galois(in, elt), or in + apply_galois(in, elt) when add_input (the "rotated = rotate(retval); retval += rotated"
+// step of accumulateCKKS / accumulateBFV, R/src/engine/seal_context.cpp:302-303,337-338, without a separate add pass:
+// g(c0) + c0 comes out of the permutation kernel and c1 rides along as the key switch's second addend)
+static int apply_galois_impl(b200he_ctx *c, const b200he_batch *in, uint32_t elt, b200he_batch *out, bool add_input)
 {
     if (!c || !in || !out) return fail("apply_galois: NULL argument");
     if (in->ctx != c || out->ctx != c) return fail("apply_galois: batch belongs to another context");
@@ -983,7 +986,7 @@ extern "C" int b200he_apply_galois(b200he_ctx *c, const b200he_batch *in, uint32
     if (!g1) return fail("apply_galois: out of device memory");
     GaloisArgs G{};
     G.src = in->d; G.dst0 = ob.ptr(); G.dst1 = g1; G.src_stride = 2 * LN; G.dst_stride = 2 * LN;
-    G.elt = elt; G.L = in->L; G.logn = c->logn; G.B = B;
+    G.elt = elt; G.L = in->L; G.logn = c->logn; G.B = B; G.add_input = add_input ? 1 : 0;
     int rc = 0;
     if (ckks) {
         rc = galois_table(c, elt, &G.table);
@@ -991,11 +994,18 @@ extern "C" int b200he_apply_galois(b200he_ctx *c, const b200he_batch *in, uint32
     } else
         LAUNCH(c, B200HE_KERN_GALOIS, k_galois_coeff, blocks_for(B * 2 * LN), 256, 0, c->T, G);
     if (!rc && cudaGetLastError() != cudaSuccess) rc = fail("apply_galois: launch failed");
-    if (!rc) rc = key_switch(c, in->L, B, g1, LN, kit->second, ob.ptr(), nullptr, 2 * LN, ob.ptr(), 2 * LN);
+    if (!rc) {
+        if (add_input) rc = key_switch(c, in->L, B, g1, LN, kit->second, ob.ptr(), in->d + LN, 2 * LN, ob.ptr(), 2 * LN);
+        else rc = key_switch(c, in->L, B, g1, LN, kit->second, ob.ptr(), nullptr, 2 * LN, ob.ptr(), 2 * LN);
+    }
     c->pool.put(g1);
     if (rc) return rc;
     ob.commit();
     return 0;
+}
+extern "C" int b200he_apply_galois(b200he_ctx *c, const b200he_batch *in, uint32_t elt, b200he_batch *out)
+{
+    return apply_galois_impl(c, in, elt, out, false);
 }
 
 // SEAL GaloisTool::get_elt_from_step
@@ -1153,13 +1163,19 @@ extern "C" int b200he_accumulate(b200he_ctx *c, b200he_batch *io, uint64_t count
     b200he_batch *tmp = nullptr;
     TRY(b200he_batch_create(c, &tmp));
     int rc = 0;
+    if (io->size != 2) { b200he_batch_destroy(tmp); return fail("rotate: ciphertext size must be 2"); }
     for (int k = 0; k < rot && !rc; k++) {
-        rc = b200he_rotate(c, io, 1 << k, tmp);
-        if (!rc) rc = b200he_add(c, io, nullptr, tmp, nullptr, io->count, io);
+        const u32 elt = elt_from_step(c, 1 << k);
+        if (elt && c->gal.count(elt)) rc = apply_galois_impl(c, io, elt, io, true);   // io += rotate(io, 2^k) in one key switch
+        else {   // no key for this power of two: SEAL's NAF fallback, then the add
+            rc = b200he_rotate(c, io, 1 << k, tmp);
+            if (!rc) rc = b200he_add(c, io, nullptr, tmp, nullptr, io->count, io);
+        }
     }
     if (!rc && !ckks && count > slots) {
-        rc = b200he_rotate_columns(c, io, tmp);
-        if (!rc) rc = b200he_add(c, io, nullptr, tmp, nullptr, io->count, io);
+        const u32 elt = 2 * c->N - 1;
+        if (c->gal.count(elt)) rc = apply_galois_impl(c, io, elt, io, true);
+        else rc = fail("apply_galois: no Galois key for element %u", elt);
     }
     b200he_batch_destroy(tmp);
     return rc;

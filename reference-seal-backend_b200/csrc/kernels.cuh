@@ -711,6 +711,7 @@ struct GaloisArgs {
     u32 elt;              // Galois element (BFV coefficient form)
     int L, logn;
     size_t B;
+    int add_input;        // dst0 = g(c0) + c0 (rotate-and-add of accumulate: the key switch then adds c1 as its second addend)
 };
 __global__ void __launch_bounds__(256) k_galois_ntt(Tables T, GaloisArgs A)
 {
@@ -720,7 +721,7 @@ __global__ void __launch_bounds__(256) k_galois_ntt(Tables T, GaloisArgs A)
     const size_t b = gid / per_ct, rem = gid % per_ct;
     const size_t p = rem / ((size_t)A.L * N), le = rem % ((size_t)A.L * N), l = le / N, e = le % N;
     const u64 v = A.src[b * A.src_stride + p * A.L * N + l * N + A.table[e]];
-    if (p == 0) A.dst0[b * A.dst_stride + le] = v;
+    if (p == 0) A.dst0[b * A.dst_stride + le] = A.add_input ? add_mod(v, A.src[b * A.src_stride + le], T.mods[l].q) : v;
     else A.dst1[b * A.L * N + le] = v;
 }
 // Coefficient-form automorphism (BFV): coefficient i moves to i*elt mod N, negated when floor(i*elt/N) is odd.
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(256) k_galois_coeff(Tables T, GaloisArgs A)
     const u64 raw = (u64)i * A.elt;
     const size_t idx = raw & (N - 1);
     if ((raw >> A.logn) & 1) v = v ? q - v : 0;
-    if (p == 0) A.dst0[b * A.dst_stride + l * N + idx] = v;
+    if (p == 0) A.dst0[b * A.dst_stride + l * N + idx] = A.add_input ? add_mod(v, A.src[b * A.src_stride + l * N + idx], q) : v;
     else A.dst1[b * A.L * N + l * N + idx] = v;
 }
 
