@@ -117,6 +117,34 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": self.n}
 
 
+def bind_to_gpu_numa_node(gpu):
+    """Pin this rank to the CPU cores of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated
+    (first-touch places them on that node), so the per-step host<->device copies of several ranks do not all cross
+    one socket's memory controller / the inter-socket link.  Best effort: returns a description or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(gpu)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]   # 0000:17:00.0
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cores)"
+    except Exception:
+        return None
+
+
 def synth_inputs(moduli, n, L, N, seed):
     import numpy as np
     rng = np.random.default_rng(seed)
@@ -171,6 +199,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     from pyb200he.shard import Ranks
     dist = None
     if world > 1:
@@ -279,6 +308,28 @@ def run_b200(args):
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
     e2e_launches = sum(cx.launch_count() for cx, _, _b in e2e)
 
+    # ---- second half of BASELINE.json's metric: NTT limb-ops/s (batched forward / inverse transforms of the same
+    # 1000 x 2 x L limbs through the C ABI), outside the timed regions above
+    C0 = ctx.batch(a_np[:1], ntt_form=False, scale=scale)
+    C0.resize(BATCH, 2, L, False, scale)
+    C0.upload_from(a_pin.data_ptr(), 0, BATCH)
+    F0, I0 = hb.Batch(ctx), hb.Batch(ctx)
+    for _ in range(2):
+        ctx.ntt_forward(C0, out=F0)
+        ctx.ntt_inverse(F0, out=I0)
+    ctx.profile_begin()
+    for _ in range(5):
+        ctx.ntt_forward(C0, out=F0)
+        ctx.ntt_inverse(F0, out=I0)
+    nprof = ctx.profile_end()
+    assert np.array_equal(I0.download(0, 1), a_np[:1]), "inverse(forward) is not the identity"
+    limbs = BATCH * 2 * L
+    fwd_s = nprof["k_ntt_fwd"][0] / nprof["k_ntt_fwd"][1] / 1e3
+    inv_s = nprof["k_ntt_inv"][0] / nprof["k_ntt_inv"][1] / 1e3
+    bfly = (N // 2) * (N.bit_length() - 1)
+    ntt_metric = {"N": N, "limbs_per_launch": limbs, "fwd_limb_ops_per_s": limbs / fwd_s, "inv_limb_ops_per_s": limbs / inv_s,
+                  "fwd_butterflies_per_s": limbs * bfly / fwd_s, "fwd_GBps_algorithmic": limbs * 2 * N * 8 / fwd_s / 1e9}
+
     # sanity: the timed path produced the bits the step defines (first result vs a fresh single-ciphertext run)
     chk = ctx.multiply(ctx.batch(a_np[:1], scale=scale), ctx.batch(b_np[:1], scale=scale))
     ctx.relinearize(chk, out=chk)        # the two separate calls: the fused entry must give the same bits
@@ -314,7 +365,7 @@ def run_b200(args):
         "config": CONFIG, "clocks": clocks,
         "e2e": {"value": samples / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * words_in * 8 * world,
                 "d2h_bytes_per_step": BATCH * words_out * 8 * world, "ms_per_step": e2e_ms / args.steps,
-                "pipeline": f"{E2E_STREAMS} streams x chunks of {CHUNK} ciphertext pairs"},
+                "pipeline": f"{E2E_STREAMS} streams x chunks of {CHUNK} ciphertext pairs", "host_binding": numa},
         "gpu_launches": launches * world,
         "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -326,6 +377,9 @@ def run_b200(args):
                                   "frac": (bf_rate / bf_peak) if bf_rate else None, "peak_source": bf_src}},
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
     }
+    ntt_metric["fwd_frac_of_butterfly_peak"] = ntt_metric["fwd_butterflies_per_s"] / bf_peak
+    ntt_metric["fwd_frac_of_hbm_peak"] = ntt_metric["fwd_GBps_algorithmic"] / peak
+    line["ntt_limb_ops"] = ntt_metric   # per GPU
     line["cpu_baseline"] = cpu_baseline(budget_s=12.0) if world == 1 else None
     print(json.dumps(line), flush=True)
     if dist is not None:

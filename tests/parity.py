@@ -284,6 +284,15 @@ def case_errors(env):
             env.ctx.add(x, y)        # different levels
     with pytest.raises(hb.B200HEError):
         env.ctx.add(x, x, ai=[3], bi=[0])   # index out of range
+    # the fused entry reports what the two calls would: last level, and size-2 input = plain rescale
+    x1 = env.batch(env.rand_ct(1, size=3, L=1), size=3, L=1)
+    with pytest.raises(hb.B200HEError):
+        env.ctx.relinearize_rescale(x1)
+    if L >= 2:
+        x2 = env.rand_ct(2, L=L)
+        eq(env.ctx.relinearize_rescale(env.batch(x2, L=L)).download(), env.ctx.rescale_to_next(env.batch(x2, L=L)).download(),
+           "relinearize_rescale on size-2 input")
+        assert env.ctx.relinearize_rescale(env.ctx.batch(np.zeros(0, dtype=np.uint64), size=3, L=L)).count == 0
     # empty batches are fine
     e = env.ctx.batch(np.zeros(0, dtype=np.uint64), L=L)
     assert env.ctx.add(e, e).count == 0

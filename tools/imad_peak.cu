@@ -113,6 +113,77 @@ template <int V> __global__ void __launch_bounds__(512) k_bfly(u64 *out, u64 w, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the same 4-stage pass with the twiddle pattern of the real kernels: 1, 2, 4, 8 distinct (w, w') pairs per stage,
+// 15 per pass, fetched from (L1-resident) global memory every pass -- register pressure like the last NTT pass
+__global__ void __launch_bounds__(512) k_bfly_tw(u64 *out, const ulonglong2 *__restrict__ tw, u64 q)
+{
+    u64 x[16];
+    const u64 nq = 0 - q, two_q = 2 * q;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = (u64)threadIdx.x * 0x9E3779B97F4A7C15ull + i;
+    for (int it = 0; it < ITERS / 4; it++) {
+        ulonglong2 t[15];
+#pragma unroll
+        for (int i = 0; i < 15; i++) t[i] = __ldg(tw + ((threadIdx.x + it) & 31) * 16 + i);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int half = 8 >> s;
+#pragma unroll
+            for (int blk = 0; blk < (1 << s); blk++) {
+                const ulonglong2 w = t[(1 << s) - 1 + blk];
+#pragma unroll
+                for (int jj = 0; jj < half; jj++) {
+                    u64 &a = x[blk * 2 * half + jj], &b = x[blk * 2 * half + jj + half];
+                    const u64 v = shoup_mad<0>(b, w.x, w.y, nq, 0);
+                    b = a + two_q - v;
+                    a = a + v;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] &= 0x0fffffffffffffffull;
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// MODE 0: per-stage twiddle and the modulus constants in VECTOR registers (loaded from global memory, as the kernels
+//         did before the constants moved to kernel parameters); 1: twiddle in vector registers, modulus constants
+//         uniform; 2: twiddle uniform, modulus constants in vector registers
+template <int MODE> __global__ void __launch_bounds__(512) k_bfly_vec(u64 *out, const ulonglong2 *__restrict__ tw, const u64 *__restrict__ mod, u64 qq)
+{
+    u64 x[16];
+    const u64 q = MODE == 1 ? qq : mod[0];
+    const u64 nq = 0 - q, two_q = 2 * q;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = (u64)threadIdx.x * 0x9E3779B97F4A7C15ull + i;
+    for (int it = 0; it < ITERS / 4; it++) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            ulonglong2 w;
+            if (MODE == 2) w = make_ulonglong2(qq + s + it, qq * 3 + s);
+            else w = __ldg(tw + ((threadIdx.x >> 5) + it + s) % 32);
+            const int half = 1 << s;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j & half) continue;
+                u64 &a = x[j], &b = x[j + half];
+                const u64 v = shoup_mad<0>(b, w.x, w.y, nq, 0);
+                b = a + two_q - v;
+                a = a + v;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] &= 0x0fffffffffffffffull;
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F> static float time_ms(F &&f)
 {
     cudaEvent_t a, b;
@@ -168,6 +239,29 @@ int main()
                (ms * 1e-3) * (clk * 1e3) * sms * 4 / (bf / 32));                                              \
     }
     RUNB(0) RUNB(1) RUNB(2) RUNB(3)
+    {
+        ulonglong2 *tw;
+        cudaMalloc(&tw, 32 * 16 * sizeof(ulonglong2));
+        cudaMemset(tw, 0x5a, 32 * 16 * sizeof(ulonglong2));
+        const int grid = sms * 4;
+        float ms = time_ms([&] { k_bfly_tw<<<grid, 512>>>((u64 *)out, tw, q); });
+        double bf = (double)grid * 512 * (ITERS / 4) * 32;
+        u64 *mod;
+        cudaMalloc(&mod, 64);
+        cudaMemcpy(mod, &q, 8, cudaMemcpyHostToDevice);
+#define RUNV(MODE, NAME)                                                                                      \
+        {                                                                                                     \
+            float ms2 = time_ms([&] { k_bfly_vec<MODE><<<grid, 512>>>((u64 *)out, tw, mod, q); });            \
+            double bf2 = (double)grid * 512 * (ITERS / 4) * 32;                                               \
+            printf(" \"" NAME "\": {\"ms\": %.4f, \"Gbfly_per_s\": %.1f, \"cycles_per_warp_bfly_per_smsp\": %.2f},\n", ms2, bf2 / ms2 / 1e6, \
+                   (ms2 * 1e-3) * (clk * 1e3) * sms * 4 / (bf2 / 32));                                        \
+        }
+        RUNV(0, "bfly_vector_twiddle_vector_modulus")
+        RUNV(1, "bfly_vector_twiddle_uniform_modulus")
+        RUNV(2, "bfly_uniform_twiddle_vector_modulus")
+        printf(" \"bfly_exact_mulhi_15_twiddles_per_pass\": {\"ms\": %.4f, \"Gbfly_per_s\": %.1f, \"cycles_per_warp_bfly_per_smsp\": %.2f},\n", ms, bf / ms / 1e6,
+               (ms * 1e-3) * (clk * 1e3) * sms * 4 / (bf / 32));
+    }
     printf(" \"note\": \"clock_khz is the attribute (max boost); lanes/clk uses it\"}\n");
     return 0;
 }
