@@ -320,7 +320,7 @@ template <int LG, int CC> static int set_smem_attrs()
     CK(cudaFuncSetAttribute(k_ntt_fwd<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_ntt_inv<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
 #endif
     return 0;
 }
@@ -901,10 +901,10 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
             if (rc) break;
             D.rp2 = rp2; D.x2 = L - 1; D.nJ = L - 1; D.out_poly_stride = (size_t)(L - 1) * N;
             KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * 2 * (L - 1)) << c->c), NttCfg<LG>::THREADS,
-                                   NttCfg<LG>::SMEM_BYTES, c->T, D));
+                                   ModDownCfg<LG>::SMEM_BYTES, c->T, D));
         } else if (ckks) {
             KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * 2 * L) << c->c), NttCfg<LG>::THREADS,
-                                   NttCfg<LG>::SMEM_BYTES, c->T, D));
+                                   ModDownCfg<LG>::SMEM_BYTES, c->T, D));
         } else {
             // BFV: accumulators back to coefficient form (in place, unsplit per-limb strides), then elementwise mod-down
             rc = ntt_inv(c, acc, acc, nb * 2 * L, (size_t)(L + 1) * N, (size_t)(L + 1) * N, L, 0, INV_PLAIN);
@@ -1214,7 +1214,7 @@ extern "C" int b200he_rescale_to_next(b200he_ctx *c, const b200he_batch *in, b20
             if (rc) break;
             D.rp = rp;
             KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * P * (L - 1)) << c->c), NttCfg<LG>::THREADS,
-                                   NttCfg<LG>::SMEM_BYTES, c->T, D));
+                                   ModDownCfg<LG>::SMEM_BYTES, c->T, D));
         } else {
             // coefficient form: rp = last + q_last/2 mod q_last, elementwise
             D.rp = nullptr; D.rp_raw = src + (size_t)(L - 1) * N; D.rp_raw_stride = (size_t)L * N;

@@ -555,12 +555,19 @@ struct ModDownArgs {
     const u64 *rp2;
     int x2;
 };
+// Shared memory: transform buffer | TMA landing zone of the accumulator tile | of the addend tile | mbarrier.
+// The two epilogue operands of a CTA are contiguous 8 NL-byte tiles; thread 0 starts their bulk copies before the
+// transform and the epilogue reads them from shared memory.
+template <int LOGN> struct ModDownCfg {
+    static constexpr int SMEM_BYTES = 3 * NttCfg<LOGN>::SMEM_BYTES + 16;
+};
 template <int LOGN, int C>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, ModDownArgs A)
 {
     constexpr int c = C;
     constexpr int NL = 1 << LOGN;
     u64 *sm = dyn_smem();
+    u64 *stage_b = sm + NL, *stage_a = sm + 2 * NL, *bar = sm + 3 * NL;
     const int tid = threadIdx.x;
     const int r = blockIdx.x & ((1 << c) - 1);
     int unit = blockIdx.x >> c;
@@ -578,6 +585,17 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
     const u64 *bp = A.base + (size_t)b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + off;
     const u64 *ap = A.addend[p] ? A.addend[p] + (size_t)b * A.add_ct_stride + (size_t)j * N + off : nullptr;
     u64 *op = A.out + (size_t)b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + off;
+    // epilogue operands: bulk copies (TMA) into shared memory, in flight during the transform.  out may alias the
+    // addend element for element (b200he_apply_galois): this CTA is the only one that touches its tile, and it has
+    // read the whole tile before it writes.
+    // (thread 0 initialises, arms and uses the barrier; everyone else first touches it after the CTA-wide barriers of
+    // the transform, which order the initialisation before their wait)
+    if (tid == 0) {
+        tma_bar_init(bar);
+        tma_bar_expect(bar, (ap ? 2u : 1u) * NL * 8);
+        tma_load_1d(stage_b, bp, NL * 8, bar);
+        if (ap) tma_load_1d(stage_a, ap, NL * 8, bar);
+    }
     if (A.rp2) {
         const ulonglong2 ri = T.qinv[(size_t)A.x2 * T.M + j];
         const u64 fix2 = m.q - T.halfmod[(size_t)A.x2 * T.M + j];
@@ -586,8 +604,9 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
         canon_all(x, m);
         contig_to_co(x, sm, tid);
+        tma_bar_wait(bar, 0);
         for_pairs_co(tid, [&](int reg, int e) {
-            const ulonglong2 bv = ldg2(bp + e), av = ldg2(ap + e);
+            const ulonglong2 bv = ld2(stage_b + e), av = ld2(stage_a + e);
             const u64 g0 = shoup_lazy(bv.x, qi.x, qi.y, m.q) + av.x, g1 = shoup_lazy(bv.y, qi.x, qi.y, m.q) + av.y;   // < 3q
             const u64 h0 = shoup(g0, ri.x, ri.y, m.q), h1 = shoup(g1, ri.x, ri.y, m.q);
             st2(op + e, sub_mod(h0, x[reg], m.q), sub_mod(h1, x[reg + 1], m.q));
@@ -598,13 +617,14 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     canon_all(x, m);
     contig_to_co(x, sm, tid);
+    tma_bar_wait(bar, 0);
     for_pairs_co(tid, [&](int reg, int e) {
-        ulonglong2 bv = ldg2(bp + e);
+        ulonglong2 bv = ld2(stage_b + e);
         u64 u0 = x[reg], u1 = x[reg + 1];
         u64 v0 = shoup(sub_mod(bv.x, u0, m.q), qi.x, qi.y, m.q);
         u64 v1 = shoup(sub_mod(bv.y, u1, m.q), qi.x, qi.y, m.q);
         if (ap) {
-            ulonglong2 av = ldg2(ap + e);
+            ulonglong2 av = ld2(stage_a + e);
             v0 = add_mod(v0, av.x, m.q);
             v1 = add_mod(v1, av.y, m.q);
         }

@@ -383,6 +383,58 @@ template <class F> __device__ __forceinline__ void for_pairs_co(int tid, F &&f)
     for (int i = 0; i < 8; i++) f(2 * i, co_elem(tid, i));
 }
 
+// ---- TMA bulk copies (cp.async.bulk) of contiguous limb tiles into shared memory, completion on an mbarrier ----
+// One elected thread arms the barrier with the byte count and issues the copies; the copy engine moves the tile while
+// the CTA computes; every thread waits on the barrier's phase right before it reads the tile.  Used for operands that
+// are needed only after a transform (the epilogue operands of k_moddown): their HBM latency disappears behind the NTT.
+__device__ __forceinline__ void tma_bar_init(u64 *bar)   // one thread; other threads may touch the barrier only after a CTA-wide barrier
+{
+#ifdef B200HE_EMU
+    *bar = 0;
+#else
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void tma_bar_expect(u64 *bar, u32 bytes)   // the issuing thread, before its copies
+{
+#ifdef B200HE_EMU
+    (void)bar; (void)bytes;
+#else
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar)   // bytes % 16 == 0, 16-byte aligned
+{
+#ifdef B200HE_EMU
+    (void)bar;
+    memcpy(smem_dst, gsrc, bytes);
+#else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (u32)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((u32)__cvta_generic_to_shared(bar))
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void tma_bar_wait(u64 *bar, u32 phase)
+{
+#ifdef B200HE_EMU
+    (void)bar; (void)phase;
+#else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((u32)__cvta_generic_to_shared(bar)),
+        "r"(phase)
+        : "memory");
+#endif
+}
+
 __device__ __forceinline__ ulonglong2 ldg2(const u64 *p)
 {
 #if defined(__CUDA_ARCH__)
