@@ -173,20 +173,25 @@ Handle LogRegHornerBenchmark::operate(Handle h_remote_packed, const ParameterInd
         throw HEBenchError(HEBERROR_MSG_CLASS("Invalid indexer range for parameter " + std::to_string(LogRegHornerBenchmarkDescription::Index_X) + " detected."),
                            HEBENCH_ECODE_INVALID_ARGS);
     SEALContextWrapper &cw = *m_p_ctx_wrapper;
-    // linear part + collapse, per GPU on its shard of the samples
-    std::vector<DeviceBatchPtr> partial(cw.gpuCount());
+    // linear part + collapse, per GPU on its shard of the samples.  Everything below only enqueues work on the GPUs'
+    // streams, except the fresh encryption of zero that GPU 0's collapse uploads (a blocking copy): GPU 0's collapse is
+    // therefore issued last, when every other GPU already has its whole share queued, so the GPUs run concurrently.
+    std::vector<DeviceBatchPtr> partial(cw.gpuCount()), dots(cw.gpuCount());
     for (int g = 0; g < cw.gpuCount(); ++g) {
         const std::uint64_t first = in.X.first[g], n = in.X.first[g + 1] - first;
-        b200he_ctx *c       = cw.device(g);
-        DeviceBatchPtr dots = cw.newBatch(g);
+        b200he_ctx *c = cw.device(g);
+        dots[g]       = cw.newBatch(g);
         if (n > 0) {
             std::vector<uint32_t> wi(n, 0);
-            cw.check(b200he_multiply(c, in.W[g]->get(), wi.data(), in.X.shard[g]->get(), nullptr, n, dots->get()), "b200he_multiply");
-            cw.check(b200he_relinearize(c, dots->get(), dots->get()), "b200he_relinearize");
-            cw.accumulateCKKS(*dots, m_w_params.n());
-            cw.check(b200he_rescale_to_next(c, dots->get(), dots->get()), "b200he_rescale_to_next");
+            cw.check(b200he_multiply(c, in.W[g]->get(), wi.data(), in.X.shard[g]->get(), nullptr, n, dots[g]->get()), "b200he_multiply");
+            cw.check(b200he_relinearize(c, dots[g]->get(), dots[g]->get()), "b200he_relinearize");
+            cw.accumulateCKKS(*dots[g], m_w_params.n());
+            cw.check(b200he_rescale_to_next(c, dots[g]->get(), dots[g]->get()), "b200he_rescale_to_next");
         }
-        if (n > 0 || g == 0) partial[g] = cw.collapseCKKS(*dots, first, batch, g == 0);
+    }
+    for (int g = cw.gpuCount() - 1; g >= 0; --g) {
+        const std::uint64_t first = in.X.first[g], n = in.X.first[g + 1] - first;
+        if (n > 0 || g == 0) partial[g] = cw.collapseCKKS(*dots[g], first, batch, g == 0);
     }
     // exchange: partial sums of the other GPUs are added on GPU 0
     DeviceBatchPtr lr = partial[0];
