@@ -225,7 +225,27 @@ static Mod make_mod(u64 q, u64 N)
     m.r64 = (u64)((((hm::u128)1) << 64) / q);
     m.ninv = hm::invmod(N % q, q);
     m.ninv_s = hm::shoup(m.ninv, q);
+    // FP64 domain for small primes (modarith.cuh); B200HE_NO_DP=1 keeps every modulus on the integer pipe (A/B timing)
+    static const bool no_dp = getenv("B200HE_NO_DP") && atoi(getenv("B200HE_NO_DP"));
+    m.dp = (m.bits <= B200HE_DP_MAX_BITS && !no_dp) ? 1 : 0;
+    m.dq = (double)q;
+    m.dnq = -m.dq;
+    m.dqinv = 1.0 / m.dq;
+    m.dqinv_up = m.dqinv;
+    if (fma(m.dqinv_up, m.dq, -1.0) < 0) m.dqinv_up = nextafter(m.dqinv_up, 2.0);   // sign of qinv*q - 1 is exact under one rounding
+    m.dninv = (double)m.ninv;
+    m.dninv_q = m.dninv / m.dq;
     return m;
+}
+// twiddle in the form the modulus' transforms consume: (w, floor(w 2^64 / q)), or (w, RN(w / q)) as doubles
+static ulonglong2 make_tw(u64 w, const Mod &m)
+{
+    if (!m.dp) return make_ulonglong2(w, hm::shoup(w, m.q));
+    const double d = (double)w, dq = d / m.dq;
+    ulonglong2 r;
+    memcpy(&r.x, &d, 8);
+    memcpy(&r.y, &dq, 8);
+    return r;
 }
 
 // Lazy-reduction schedule of the CTA-local transforms for one modulus (see ntt_core.cuh bfly_fwd /
@@ -256,6 +276,7 @@ template <int LG> static void lazy_schedule(Mod &m, int c, int L_top)
     // key-switch inner product: every digit adds a Shoup product < 2q to the accumulators
     const u64 period = bmax >= 4 ? (bmax - 2) / 2 : 1;
     m.acc_period = (u32)(period > (u64)L_top + 1 ? (u64)L_top + 1 : period);
+    if (m.dp) m.acc_period = 16;   // FP64 domain: 0.75 q per digit, dp_canon accepts magnitudes up to 16 q
 }
 
 static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std::vector<u64> &psi)
@@ -270,17 +291,17 @@ static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std
         c->mods[i] = make_mod(q, N);
         NTT_DISPATCH(c, lazy_schedule<LG>(c->mods[i], c->c, (int)c->K));
         const u64 ipsi = hm::invmod(psi[i], q);
-        u64 p = 1, ip = 1;
+        u64 p = 1, ip = 1, ipsi_half = 0;
         for (size_t k = 0; k < N; k++) {
             const size_t r = hm::brv((uint32_t)k, c->logn);
-            tw[i * N + r] = make_ulonglong2(p, hm::shoup(p, q));
-            itw[i * N + r] = make_ulonglong2(ip, hm::shoup(ip, q));
+            tw[i * N + r] = make_tw(p, c->mods[i]);
+            itw[i * N + r] = make_tw(ip, c->mods[i]);
+            if (r == 1) ipsi_half = ip;
             p = hm::mulmod(p, psi[i], q);
             ip = hm::mulmod(ip, ipsi, q);
         }
         // slot 0 (the unused psi^0) carries the last inverse stage's twiddle with N^{-1} folded in
-        const u64 w = hm::mulmod(itw[i * N + 1].x, c->mods[i].ninv, q);
-        itw[i * N] = make_ulonglong2(w, hm::shoup(w, q));
+        itw[i * N] = make_tw(hm::mulmod(ipsi_half, c->mods[i].ninv, q), c->mods[i]);
         for (size_t x = 0; x < M; x++) {
             const u64 qx = moduli[x];
             u64 inv = (x == i) ? 0 : hm::invmod(qx % q, q);

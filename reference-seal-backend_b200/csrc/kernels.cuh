@@ -79,6 +79,12 @@ struct PreTwo {
 // lazy Cooley-Tukey butterfly used by the split pre-stages (bound of both outputs: bound(a) + 2q)
 __device__ __forceinline__ void ct_lazy(u64 &a, u64 &b, ulonglong2 w, const Mod &m)
 {
+    if (m.dp) {   // FP64 domain (modarith.cuh): magnitudes grow by 0.75 q
+        const double av = as_d(a), v = dp_mul(as_d(b), as_d(w.x), as_d(w.y), m.dnq);
+        b = as_u(__dadd_rn(av, -v));
+        a = as_u(__dadd_rn(av, v));
+        return;
+    }
     const u64 v = shoup_mad(b, w.x, w.y, m.nq, 0);
     b = a + m.two_q - v;
     a = a + v;
@@ -134,19 +140,27 @@ __device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, i
     cross_publish<LOGN>(x, sm, c, r, tid);
     cluster_sync();
     if (c == 1) {
+        // CTA r owns register pairs [4r, 4r + 4): pair i of those sits at offset base + (4r + i) G.  All four peer
+        // values are requested before the first is used (DSMEM latency paid once); the own operands are selected
+        // from the two candidate register groups so that no register index depends on r.
+        typedef Pass<LOGN, 0> G0;
+        // (limbs are split only into chunks of 8192 coefficients -- KERNEL_DISPATCH -- whose first pass holds 8 rows x 2 columns)
         u64 *peer = cluster_peer(sm, r ^ 1);
         const ulonglong2 w = ld_tw(tw + 1);
-        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            if (reg / own != r) return;
-            const ulonglong2 pv = ld2(peer + swz(e));
-            u64 a0 = r ? pv.x : x[reg], a1 = r ? pv.y : x[reg + 1];   // chunk 0
-            u64 b0 = r ? x[reg] : pv.x, b1 = r ? x[reg + 1] : pv.y;   // chunk 1
+        ulonglong2 pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) pv[i] = ld2(peer + swz(G0::elem(tid, 4 * r + i, 0)));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u64 o0 = r ? x[8 + 2 * i] : x[2 * i], o1 = r ? x[9 + 2 * i] : x[2 * i + 1];
+            u64 a0 = r ? pv[i].x : o0, a1 = r ? pv[i].y : o1;   // chunk 0
+            u64 b0 = r ? o0 : pv[i].x, b1 = r ? o1 : pv[i].y;   // chunk 1
             ct_lazy(a0, b0, w, m);
             ct_lazy(a1, b1, w, m);
-            x[reg] = r ? b0 : a0;
-            x[reg + 1] = r ? b1 : a1;
-            st2(peer + swz(e), r ? a0 : b0, r ? a1 : b1);
-        });
+            st2(peer + swz(G0::elem(tid, 4 * r + i, 0)), r ? a0 : b0, r ? a1 : b1);
+            if (r) { x[8 + 2 * i] = b0; x[9 + 2 * i] = b1; }
+            else { x[2 * i] = a0; x[2 * i + 1] = a1; }
+        }
     } else {
         u64 *peer[4];
 #pragma unroll
@@ -178,8 +192,33 @@ __device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, i
     cross_collect<LOGN>(x, sm, c, r, tid);
 }
 
+// final cross-chunk stage of the inverse: (a + b) N^{-1} and (a - b) wn, results in [0, 2q) as integers (either domain)
+__device__ __forceinline__ void inv_last(u64 a, u64 b, ulonglong2 wn, const Mod &m, u64 &s, u64 &d)
+{
+    if (m.dp) {
+        const double av = as_d(a), bv = as_d(b);
+        s = dp_canon(dp_mul(__dadd_rn(av, bv), m.dninv, m.dninv_q, m.dnq), m);
+        d = dp_canon(dp_mul(__dadd_rn(av, -bv), as_d(wn.x), as_d(wn.y), m.dnq), m);
+        return;
+    }
+    s = shoup_lazy(a + b, m.ninv, m.ninv_s, m.q);
+    d = shoup_lazy(a - b + m.two_q, wn.x, wn.y, m.q);
+}
+// Gentleman-Sande butterfly of the cross-chunk stages: inputs reduced (reduce_all), either domain
+__device__ __forceinline__ void gs_cross(u64 &x, u64 &y, ulonglong2 w, const Mod &m)
+{
+    if (m.dp) {
+        const double av = as_d(x), bv = as_d(y);
+        x = as_u(__dadd_rn(av, bv));
+        y = as_u(dp_mul(__dadd_rn(av, -bv), as_d(w.x), as_d(w.y), m.dnq));
+        return;
+    }
+    gs_bfly(x, y, w.x, w.y, m.q, m.two_q);
+}
+
 // Last c Gentleman-Sande stages across the chunks of a cluster, with N^{-1} folded into the final one.
-// In: x = pass-0 layout of chunk r after the local stages, reduced to [0, 2q).  Out: finished values in [0, 2q).
+// In: x = pass-0 layout of chunk r after the local stages, reduced (reduce_all: [0, 2q), or |x| <= q/2 in the FP64
+// domain).  Out: finished values in [0, 2q), integers in either domain.
 template <int LOGN>
 __device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, int tid, const ulonglong2 *__restrict__ itw, const Mod &m)
 {
@@ -188,17 +227,23 @@ __device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, i
     cluster_sync();
     const ulonglong2 wn = ld_tw(itw);
     if (c == 1) {
+        typedef Pass<LOGN, 0> G0;
+        // (limbs are split only into chunks of 8192 coefficients -- KERNEL_DISPATCH -- whose first pass holds 8 rows x 2 columns)
         u64 *peer = cluster_peer(sm, r ^ 1);
-        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            if (reg / own != r) return;
-            const ulonglong2 pv = ld2(peer + swz(e));
-            const u64 a0 = r ? pv.x : x[reg], a1 = r ? pv.y : x[reg + 1], b0 = r ? x[reg] : pv.x, b1 = r ? x[reg + 1] : pv.y;
-            const u64 s0 = shoup_lazy(a0 + b0, m.ninv, m.ninv_s, m.q), s1 = shoup_lazy(a1 + b1, m.ninv, m.ninv_s, m.q);
-            const u64 d0 = shoup_lazy(a0 - b0 + m.two_q, wn.x, wn.y, m.q), d1 = shoup_lazy(a1 - b1 + m.two_q, wn.x, wn.y, m.q);
-            x[reg] = r ? d0 : s0;
-            x[reg + 1] = r ? d1 : s1;
-            st2(peer + swz(e), r ? s0 : d0, r ? s1 : d1);
-        });
+        ulonglong2 pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) pv[i] = ld2(peer + swz(G0::elem(tid, 4 * r + i, 0)));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u64 o0 = r ? x[8 + 2 * i] : x[2 * i], o1 = r ? x[9 + 2 * i] : x[2 * i + 1];
+            const u64 a0 = r ? pv[i].x : o0, a1 = r ? pv[i].y : o1, b0 = r ? o0 : pv[i].x, b1 = r ? o1 : pv[i].y;
+            u64 s0, s1, d0, d1;
+            inv_last(a0, b0, wn, m, s0, d0);
+            inv_last(a1, b1, wn, m, s1, d1);
+            st2(peer + swz(G0::elem(tid, 4 * r + i, 0)), r ? s0 : d0, r ? s1 : d1);
+            if (r) { x[8 + 2 * i] = d0; x[9 + 2 * i] = d1; }
+            else { x[2 * i] = s0; x[2 * i + 1] = s1; }
+        }
     } else {
         u64 *peer[4];
 #pragma unroll
@@ -213,12 +258,10 @@ __device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, i
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 u64 a0 = h ? v[0].y : v[0].x, a1 = h ? v[1].y : v[1].x, a2 = h ? v[2].y : v[2].x, a3 = h ? v[3].y : v[3].x;
-                gs_bfly(a0, a1, w2.x, w2.y, m.q, m.two_q);
-                gs_bfly(a2, a3, w3.x, w3.y, m.q, m.two_q);
-                o[0][h] = shoup_lazy(a0 + a2, m.ninv, m.ninv_s, m.q);
-                o[2][h] = shoup_lazy(a0 - a2 + m.two_q, wn.x, wn.y, m.q);
-                o[1][h] = shoup_lazy(a1 + a3, m.ninv, m.ninv_s, m.q);
-                o[3][h] = shoup_lazy(a1 - a3 + m.two_q, wn.x, wn.y, m.q);
+                gs_cross(a0, a1, w2, m);
+                gs_cross(a2, a3, w3, m);
+                inv_last(a0, a2, wn, m, o[0][h], o[2][h]);
+                inv_last(a1, a3, wn, m, o[1][h], o[3][h]);
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -232,7 +275,8 @@ __device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, i
 }
 
 // Load the pass-0 register layout of chunk r of a limb (src points at the limb, N = NL << c coefficients), apply the
-// input transform, and run the c cross-chunk stages.  pre.pair() must return values < 2q; the result is < (2 + 2c) q.
+// input transform, and run the c cross-chunk stages.  pre.pair() must return values < 2q; the result is < (2 + 2c) q
+// (Mod::dp moduli: converted to the FP64 domain right after the load).
 // REUSE: the CTA has used the transform buffer before (see ntt_fwd_regs_split).
 template <int LOGN, bool REUSE = false, class Pre>
 __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restrict__ src, int c, int r, int tid,
@@ -245,6 +289,7 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
         x[reg] = v.x;
         x[reg + 1] = v.y;
     });
+    if (m.dp) to_dp_all(x);
     if (c > 0) {
         if (REUSE) __syncthreads();
         cross_fwd<LOGN>(x, sm, c, r, tid, tw, m);
@@ -385,24 +430,24 @@ struct KsInnerArgs {
     u64 *rp;               // [B][2][N]: rounded special-prime limb in coefficient form
     int L, K, B;           // B = ciphertexts in this launch
 };
+// lazy accumulator of the inner product (either domain) -> canonical residue
+__device__ __forceinline__ u64 acc_finish(u64 a, const Mod &m) { return m.dp ? dp_canon(as_d(a), m) : reduce_full(a, m); }
 template <int LOGN> struct KsCfg {
     static constexpr int SMEM_BYTES = 3 * NttCfg<LOGN>::SMEM_BYTES;   // transform buffer + 2 accumulator limbs
 };
-template <int LOGN, int C>
-__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T, KsInnerArgs A)
+// DP = Mod::dp of the CTA's modulus as a compile-time constant: the kernel branches once, at the top, into one of two
+// complete instances of the body, so the integer and the FP64-domain code never share live ranges (with the branch
+// inside the multiply-accumulate loop the register allocator spilled in both).
+template <int LOGN, int C, bool DP>
+__device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs &A, Mod m, int b, int I, int ki, int r)
 {
     constexpr int c = C;
     constexpr int NL = 1 << LOGN, TH = NttCfg<LOGN>::THREADS;
+    m.dp = DP;
     u64 *sm = dyn_smem();
     u64 *acc_sm[2] = { sm + NL, sm + 2 * NL };
     const int tid = threadIdx.x;
-    const int r = blockIdx.x & ((1 << c) - 1);
-    const int unit = blockIdx.x >> c;
-    // the special-prime units (longest: they also run the fused inverse transforms) are scheduled first
     const int L = A.L;
-    const int b = unit < A.B ? unit : (unit - A.B) / L, I = unit < A.B ? L : (unit - A.B) % L;
-    const int ki = (I == L) ? A.K - 1 : I;
-    const Mod m = T.mods[ki];
     const ulonglong2 *tw = T.tw + (size_t)ki * T.N;
     const size_t N = T.N, off = (size_t)r * NL;
 #pragma unroll
@@ -412,6 +457,18 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
     }
     for (int J = 0; J < L; J++) {
         u64 x[16];
+        // device key layout (key_word_index): per limb and chunk [p][tid][k(e), k(e+1), k'(e), k'(e+1)], e = 16 tid + 2p,
+        // k' = Shoup quotient; FP64-domain limbs [p][tid][k(e), k(e+1)] as doubles (first half of the limb's 2N-word
+        // slot): a warp's loads cover 1 KiB / 512 B of contiguous memory per p
+        const u64 *kp0 = A.key + 2 * ((((size_t)J * 2 + 0) * A.K + ki) * N + off) + (DP ? 2 : 4) * tid;
+        const u64 *kp1 = A.key + 2 * ((((size_t)J * 2 + 1) * A.K + ki) * N + off) + (DP ? 2 : 4) * tid;
+        ulonglong2 kd0[8];   // DP: key component 0, requested before the last pass of the transform
+        auto prefetch_key0 = [&]() {
+            if constexpr (DP) {
+#pragma unroll
+                for (int p = 0; p < 8; p++) kd0[p] = ldg2(kp0 + (size_t)p * 2 * TH);
+            }
+        };
         if (A.target && I == J) {
             const u64 *tp = A.target + (size_t)b * A.target_stride + (size_t)J * N + off;
             for_pairs_co(tid, [&](int reg, int e) {
@@ -419,8 +476,10 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
                 x[reg] = v.x;
                 x[reg + 1] = v.y;
             });
+            prefetch_key0();
             __syncthreads();   // the transform buffer may still be read by the previous digit's transform
             co_to_contig(x, sm, tid);
+            if (m.dp) to_dp_all(x);
         } else {
             const u64 *tp = A.tcoef + (size_t)b * A.tcoef_stride + (size_t)J * N;
             TwRegs<LOGN, 0> t0;
@@ -429,36 +488,60 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
                 load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce{ m.q, m.r64 }, sm);
             else
                 load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
-            ntt_fwd_regs_split<LOGN, true>(x, sm, tw, m, tid, c, r, t0);
+            ntt_fwd_regs_split<LOGN, true>(x, sm, tw, m, tid, c, r, t0, prefetch_key0);
         }
+        // x: the digit in NTT form, lazy (any 64-bit value congruent to it, or an FP64-domain value of magnitude < 14 q)
         const bool fold = ((J + 1) % (int)m.acc_period) == 0;
+        if constexpr (DP) {
+            // FP64 domain: the key is one double per coefficient; the quotient estimate RN(k / q) that dp_mul wants is
+            // replaced by RN(k * RN(1/q)) computed here (relative error 2^-52 instead of 2^-53: the result stays below
+            // 0.75 q for |x| < 2^50), which halves the key bytes streamed from L2.  Accumulators grow by 0.75 q per digit.
+            ulonglong2 kd1[8];
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            // device key layout (key_limb_index): per limb and chunk [p][tid][k(e), k(e+1), k'(e), k'(e+1)], e = 16 tid + 2p,
-            // k' = Shoup quotient: a warp's loads cover 1 KiB of contiguous memory per p
-            const u64 *kp = A.key + 2 * ((((size_t)J * 2 + k) * A.K + ki) * N + off) + 4 * tid;
-            ulonglong2 kv[8], ks[8], a[8];
+            for (int p = 0; p < 8; p++) kd1[p] = ldg2(kp1 + (size_t)p * 2 * TH);   // in flight during component 0
 #pragma unroll
-            for (int p = 0; p < 8; p++) {   // all 16 key loads in flight before the first use
-                kv[p] = ldg2(kp + (size_t)p * 4 * TH);
-                ks[p] = ldg2(kp + (size_t)p * 4 * TH + 2);
-            }
-#pragma unroll
-            for (int p = 0; p < 8; p++) a[p] = ld2(acc_sm[k] + (p * TH + tid) * 2);
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                a[p].x = shoup_mad(x[2 * p], kv[p].x, ks[p].x, m.nq, a[p].x);
-                a[p].y = shoup_mad(x[2 * p + 1], kv[p].y, ks[p].y, m.nq, a[p].y);
-            }
-            if (fold) {
+            for (int k = 0; k < 2; k++) {
 #pragma unroll
                 for (int p = 0; p < 8; p++) {
-                    a[p].x = reduce_lazy(a[p].x, m);
-                    a[p].y = reduce_lazy(a[p].y, m);
+                    const ulonglong2 kv = k ? kd1[p] : kd0[p];
+                    ulonglong2 a = ld2(acc_sm[k] + (p * TH + tid) * 2);
+                    const double k0 = as_d(kv.x), k1 = as_d(kv.y);
+                    double a0 = __dadd_rn(as_d(a.x), dp_mul(as_d(x[2 * p]), k0, __dmul_rn(k0, m.dqinv), m.dnq));
+                    double a1 = __dadd_rn(as_d(a.y), dp_mul(as_d(x[2 * p + 1]), k1, __dmul_rn(k1, m.dqinv), m.dnq));
+                    if (fold) {
+                        a0 = dp_reduce(a0, m.dqinv, m.dnq);
+                        a1 = dp_reduce(a1, m.dqinv, m.dnq);
+                    }
+                    st2(acc_sm[k] + (p * TH + tid) * 2, as_u(a0), as_u(a1));
                 }
             }
+        } else {
 #pragma unroll
-            for (int p = 0; p < 8; p++) st2(acc_sm[k] + (p * TH + tid) * 2, a[p].x, a[p].y);
+            for (int k = 0; k < 2; k++) {
+                const u64 *kp = k ? kp1 : kp0;
+                ulonglong2 kv[8], ks[8], a[8];
+#pragma unroll
+                for (int p = 0; p < 8; p++) {   // all 16 key loads in flight before the first use
+                    kv[p] = ldg2(kp + (size_t)p * 4 * TH);
+                    ks[p] = ldg2(kp + (size_t)p * 4 * TH + 2);
+                }
+#pragma unroll
+                for (int p = 0; p < 8; p++) a[p] = ld2(acc_sm[k] + (p * TH + tid) * 2);
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    a[p].x = shoup_mad(x[2 * p], kv[p].x, ks[p].x, m.nq, a[p].x);
+                    a[p].y = shoup_mad(x[2 * p + 1], kv[p].y, ks[p].y, m.nq, a[p].y);
+                }
+                if (fold) {
+#pragma unroll
+                    for (int p = 0; p < 8; p++) {
+                        a[p].x = reduce_lazy(a[p].x, m);
+                        a[p].y = reduce_lazy(a[p].y, m);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 8; p++) st2(acc_sm[k] + (p * TH + tid) * 2, a[p].x, a[p].y);
+            }
         }
         // no barrier here: the accumulator slots are thread-private, and the transform buffer is protected by the
         // barrier in front of its next first store (REUSE)
@@ -472,8 +555,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
             load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, (1 << c) + r);
             for_pairs_contig(tid, [&](int reg, int e) {
                 const ulonglong2 a = ld2(acc_sm[k] + ((reg >> 1) * TH + tid) * 2);
-                x[reg] = reduce_full(a.x, m);
-                x[reg + 1] = reduce_full(a.y, m);
+                x[reg] = acc_finish(a.x, m);
+                x[reg + 1] = acc_finish(a.y, m);
             });
             if (c == 0)
                 ntt_inv_regs_split<LOGN, true, true>(x, sm, itw, m, tid, 0, 0, tl);
@@ -494,17 +577,31 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T,
         u64 x[16];
         for_pairs_contig(tid, [&](int reg, int) {
             const ulonglong2 a = ld2(acc_sm[k] + ((reg >> 1) * TH + tid) * 2);
-            x[reg] = reduce_full(a.x, m);
-            x[reg + 1] = reduce_full(a.y, m);
+            x[reg] = acc_finish(a.x, m);
+            x[reg + 1] = acc_finish(a.y, m);
         });
         contig_to_co(x, sm, tid);
         for_pairs_co(tid, [&](int reg, int e) { st2(o + e, x[reg], x[reg + 1]); });
         warp_sync();   // the slice is rewritten by the next component
     }
 }
+template <int LOGN, int C>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T, KsInnerArgs A)
+{
+    const int r = blockIdx.x & ((1 << C) - 1);
+    const int unit = blockIdx.x >> C;
+    // the special-prime units (longest: they also run the fused inverse transforms) are scheduled first
+    const int L = A.L;
+    const int b = unit < A.B ? unit : (unit - A.B) / L, I = unit < A.B ? L : (unit - A.B) % L;
+    const int ki = (I == L) ? A.K - 1 : I;
+    const Mod m = T.mods[ki];
+    if (m.dp) ks_inner_body<LOGN, C, true>(T, A, m, b, I, ki, r);
+    else ks_inner_body<LOGN, C, false>(T, A, m, b, I, ki, r);
+}
 
 // Device form of a key-switching key, built once per upload from SEAL's [Ltop][2][K][N] array: every limb becomes
-// 2N words holding the key residues interleaved with their Shoup quotients floor(k * 2^64 / q) in the order
+// 2N words holding the key residues interleaved with their Shoup quotients floor(k * 2^64 / q) (FP64-domain moduli:
+// the residues as doubles, N words) in the order
 // k_ks_inner consumes them -- chunk r of NL = 16*TH coefficients, then [p][tid][k(e), k(e+1), k'(e), k'(e+1)] with
 // e = 16 tid + 2p -- so the inner product reads the key with fully coalesced 128-bit loads.
 // (restoring division, 64 steps: k < q < 2^61 so the running remainder never overflows).
@@ -518,9 +615,15 @@ __global__ void __launch_bounds__(256) k_shoup_quotients(Tables T, const u64 *__
 {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= words) return;
-    const u64 q = T.mods[(gid / T.N) % K].q;
+    const Mod &m = T.mods[(gid / T.N) % K];
+    const u64 q = m.q;
     const size_t o = key_word_index(gid / T.N, gid % T.N, T.N, lognl);
     u64 rem = key[gid], quot = 0;
+    if (m.dp) {   // FP64-domain modulus: the residue as a double, [p][tid][2] in the first half of the limb's slot
+        const size_t e = gid % T.N, NL = (size_t)1 << lognl, TH = NL / 16, el = e & (NL - 1);
+        dkey[2 * ((gid / T.N) * T.N + (e >> lognl) * NL) + (((el & 15) >> 1) * TH + (el >> 4)) * 2 + (el & 1)] = as_u(dp_from(rem));
+        return;
+    }
     dkey[o] = rem;
 #pragma unroll 1
     for (int i = 0; i < 64; i++) {

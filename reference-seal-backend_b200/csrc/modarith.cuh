@@ -39,7 +39,9 @@ struct Mod {
     u32 fwd_mask, inv_mask;
     u32 inv_c[4];   // inverse: bound multiplier C (values < C*q) at the start of pass P
     u32 acc_period; // key-switch inner product: reduce the lazy accumulators every acc_period digits
-    u32 pad_;
+    u32 dp;         // 1: the transforms of this modulus run in the FP64 domain (q < 2^DP_MAX_BITS, see below)
+    double dq, dnq, dqinv, dqinv_up;   // q, -q, RN(1/q), 1/q rounded up
+    double dninv, dninv_q;             // N^{-1} mod q and RN(N^{-1}/q)
 };
 
 __host__ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b)
@@ -115,6 +117,46 @@ __host__ __device__ __forceinline__ u64 mad_mod(u64 a, u64 b, u64 c, const Mod &
     lo += c;
     hi += (lo < c);
     return reduce128(hi, lo, m);
+}
+
+// ------------------------------------------------------------------------------------ FP64 domain
+// B200 (sm_100a) keeps a full-rate FP64 unit: DFMA issues at 64 lanes/clk/SM, twice the rate of IMAD.WIDE, and one
+// DFMA multiplies 53 x 53 bits where IMAD.WIDE multiplies 32 x 32 (tools/fp64_peak.cu, profiles/r1i_fp64_peak.json:
+// a complete butterfly costs 19 cycles per warp in FP64 against 37 on the integer pipe).  For primes below
+// 2^DP_MAX_BITS the transforms therefore compute on exact integers held in doubles, in a symmetric lazy
+// representation (any integer congruent to the residue, magnitude < 2^51):
+//   * w*y: (h, l) = two-product by FMA (h + l = w*y exactly), quotient k = rint(y * RN(w/q)) through the 1.5*2^52
+//     rounding constant, result (h - k q) + l -- both steps exact -- an integer of magnitude <= 0.75 q;
+//   * sums and differences of such values are exact as long as they stay below 2^53;
+//   * leaving the domain: floor division by q with a directed-rounding FMA (1/q rounded up, operand made positive),
+//     which is exact, then the integer is read from the mantissa.
+// Every operation is exact integer arithmetic, so results are bit-identical to the integer path.
+#define B200HE_DP_MAX_BITS 46
+#define B200HE_DP_MAGIC 6755399441055744.0   /* 1.5 * 2^52 */
+#define B200HE_DP_TWO52 4503599627370496.0
+__device__ __forceinline__ double as_d(u64 v) { return __longlong_as_double((long long)v); }
+__device__ __forceinline__ u64 as_u(double d) { return (u64)__double_as_longlong(d); }
+// integer < 2^52 -> double (exact)
+__device__ __forceinline__ double dp_from(u64 x) { return __dadd_rn(as_d(x | 0x4330000000000000ull), -B200HE_DP_TWO52); }
+// w*y mod q + e q, |result| <= 0.75 q, for |y| < 2^51; wq = RN(w/q), nq = -q
+__device__ __forceinline__ double dp_mul(double y, double w, double wq, double nq)
+{
+    const double h = __dmul_rn(y, w);
+    const double l = __fma_rn(y, w, -h);
+    const double k = __dadd_rn(__fma_rn(y, wq, B200HE_DP_MAGIC), -B200HE_DP_MAGIC);
+    return __dadd_rn(__fma_rn(k, nq, h), l);
+}
+// x - rint(x/q) q: magnitude <= q/2 + 1, for |x| < 2^51
+__device__ __forceinline__ double dp_reduce(double x, double qinv, double nq)
+{
+    return __fma_rn(__dadd_rn(__fma_rn(x, qinv, B200HE_DP_MAGIC), -B200HE_DP_MAGIC), nq, x);
+}
+// lazy value (|x| <= 16 q) -> canonical residue in [0, q) as an integer
+__device__ __forceinline__ u64 dp_canon(double x, const Mod &m)
+{
+    const double a = __fma_rn(16.0, m.dq, x);                                           // > 0, exact
+    const double k = __dadd_rn(__fma_rd(a, m.dqinv_up, B200HE_DP_MAGIC), -B200HE_DP_MAGIC);   // floor(a / q)
+    return as_u(__fma_rn(k, m.dnq, __dadd_rn(a, B200HE_DP_TWO52))) & 0x000fffffffffffffull;
 }
 
 // Harvey lazy Cooley-Tukey butterfly: x,y in [0,4q) -> [0,4q)

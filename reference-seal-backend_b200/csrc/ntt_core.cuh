@@ -160,8 +160,19 @@ template <int LOGN, int P, bool INVERSE> __device__ __forceinline__ void load_tw
     else load_tw_range<LOGN, P, TwSplit<K>::FWD_EARLY_END, K>(t, tw, tid, pre);
 }
 
+// integers (< 2^52) -> FP64 domain, in place (bit patterns of doubles in the same registers)
+__device__ __forceinline__ void to_dp_all(u64 (&x)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = as_u(dp_from(x[i]));
+}
 __device__ __forceinline__ void reduce_all(u64 (&x)[16], const Mod &m)
 {
+    if (m.dp) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = as_u(dp_reduce(as_d(x[i]), m.dqinv, m.dnq));
+        return;
+    }
     if (m.bits > 32) {
 #pragma unroll
         for (int i = 0; i < 16; i++) x[i] = reduce_lazy_t<true>(x[i], m);
@@ -170,9 +181,14 @@ __device__ __forceinline__ void reduce_all(u64 (&x)[16], const Mod &m)
         for (int i = 0; i < 16; i++) x[i] = reduce_lazy_t<false>(x[i], m);
     }
 }
-// all 16 registers -> canonical residues
+// all 16 registers (lazy output of a forward transform, either domain) -> canonical residues as integers
 __device__ __forceinline__ void canon_all(u64 (&x)[16], const Mod &m)
 {
+    if (m.dp) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = dp_canon(as_d(x[i]), m);
+        return;
+    }
     reduce_all(x, m);
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = csub(x[i], m.q);
@@ -183,10 +199,43 @@ __device__ __forceinline__ void canon_all(u64 (&x)[16], const Mod &m)
 // accepts ANY 64-bit y.  Nothing is reduced per butterfly: the bound of every value grows by 2q per
 // stage and the host-built schedule (Mod::fwd_mask) says where a pass must first pull the registers
 // back to [0,2q) so that nothing reaches 2^64.
+// FP64 domain (Mod::dp): the same pass on exact integers in doubles.  X = x + v, Y = x - v with |v| <= 0.75 q from
+// dp_mul; magnitudes grow by 0.75 q per stage (< 14 q after 15 stages from inputs < 2q), so nothing is ever reduced.
+template <int LOGN, int P>
+__device__ __forceinline__ void bfly_fwd_dp(u64 (&x)[16], TwRegs<LOGN, P> &t, const Mod &m, const ulonglong2 *__restrict__ tw, int tid, int pre)
+{
+    typedef Pass<LOGN, P> G;
+    const double nq = m.dnq;
+#pragma unroll
+    for (int u = 0; u < G::K; u++) {
+        if (u == 1) load_tw_late<LOGN, P, false>(t, tw, tid, pre);
+        const int half = 1 << (G::K - 1 - u);
+#pragma unroll
+        for (int blk = 0; blk < (1 << u); blk++) {
+            const ulonglong2 w = t.w[(1 << u) - 1 + blk];
+#pragma unroll
+            for (int jj = 0; jj < half; jj++) {
+                const int j0 = blk * 2 * half + jj, j1 = j0 + half;
+#pragma unroll
+                for (int c = 0; c < G::C; c++) {
+                    u64 &a = x[j0 * G::C + c], &b = x[j1 * G::C + c];
+                    const double av = as_d(a), v = dp_mul(as_d(b), as_d(w.x), as_d(w.y), nq);
+                    b = as_u(__dadd_rn(av, -v));
+                    a = as_u(__dadd_rn(av, v));
+                }
+            }
+        }
+    }
+}
+
 template <int LOGN, int P>
 __device__ __forceinline__ void bfly_fwd(u64 (&x)[16], TwRegs<LOGN, P> &t, const Mod &m, const ulonglong2 *__restrict__ tw, int tid, int pre)
 {
     typedef Pass<LOGN, P> G;
+    if (m.dp) {
+        bfly_fwd_dp<LOGN, P>(x, t, m, tw, tid, pre);
+        return;
+    }
     if ((m.fwd_mask >> P) & 1) reduce_all(x, m);
     const bool mid = (m.fwd_mask >> (8 + P)) & 1;
     const u64 nq = m.nq, two_q = m.two_q;
@@ -217,11 +266,58 @@ __device__ __forceinline__ void bfly_fwd(u64 (&x)[16], TwRegs<LOGN, P> &t, const
 // back to [0,2q) while the X path doubles its bound per stage (schedule: Mod::inv_mask / inv_c).
 // FINAL: this pass ends with global stage 0, into which N^{-1} is folded
 // (itw[0] holds (w1^{-1} * N^{-1}, shoup) for that purpose); outputs are then in [0,2q).
+// FP64 domain: X = x + y doubles its magnitude per stage, Y = w (x - y) comes back to 0.75 q.  Every pass but the
+// first (canonical inputs) starts with dp_reduce (|x| <= q/2), so a 4-stage pass peaks at 16 q < 2^50.
+template <int LOGN, int P, bool FINAL>
+__device__ __forceinline__ void bfly_inv_dp(u64 (&x)[16], TwRegs<LOGN, P> &t, const Mod &m, ulonglong2 wfold, const ulonglong2 *__restrict__ itw, int tid, int pre)
+{
+    typedef Pass<LOGN, P> G;
+    constexpr bool FOLD = FINAL && P == 0;
+    if (P != Sched<LOGN>::NP - 1) reduce_all(x, m);
+    const double nq = m.dnq;
+#pragma unroll
+    for (int u = G::K - 1; u >= (FOLD ? 1 : 0); u--) {
+        if (u == G::K - 2) load_tw_late<LOGN, P, true>(t, itw, tid, pre);
+        const int half = 1 << (G::K - 1 - u);
+#pragma unroll
+        for (int blk = 0; blk < (1 << u); blk++) {
+            const ulonglong2 w = t.w[(1 << u) - 1 + blk];
+#pragma unroll
+            for (int jj = 0; jj < half; jj++) {
+                const int j0 = blk * 2 * half + jj, j1 = j0 + half;
+#pragma unroll
+                for (int c = 0; c < G::C; c++) {
+                    u64 &a = x[j0 * G::C + c], &b = x[j1 * G::C + c];
+                    const double av = as_d(a), bv = as_d(b);
+                    a = as_u(__dadd_rn(av, bv));
+                    b = as_u(dp_mul(__dadd_rn(av, -bv), as_d(w.x), as_d(w.y), nq));
+                }
+            }
+        }
+    }
+    if constexpr (FOLD) {
+        constexpr int half = 1 << (G::K - 1);
+#pragma unroll
+        for (int jj = 0; jj < half; jj++)
+#pragma unroll
+            for (int c = 0; c < G::C; c++) {
+                u64 &a = x[jj * G::C + c], &b = x[(jj + half) * G::C + c];
+                const double av = as_d(a), bv = as_d(b);
+                a = as_u(dp_mul(__dadd_rn(av, bv), m.dninv, m.dninv_q, nq));
+                b = as_u(dp_mul(__dadd_rn(av, -bv), as_d(wfold.x), as_d(wfold.y), nq));
+            }
+    }
+}
+
 template <int LOGN, int P, bool FINAL>
 __device__ __forceinline__ void bfly_inv(u64 (&x)[16], TwRegs<LOGN, P> &t, const Mod &m, ulonglong2 wfold, const ulonglong2 *__restrict__ itw, int tid, int pre)
 {
     typedef Pass<LOGN, P> G;
     constexpr bool FOLD = FINAL && P == 0;
+    if (m.dp) {
+        bfly_inv_dp<LOGN, P, FINAL>(x, t, m, wfold, itw, tid, pre);
+        return;
+    }
     if ((m.inv_mask >> P) & 1) reduce_all(x, m);
     const bool mid = (m.inv_mask >> (8 + P)) & 1;
     const u64 nq = m.nq;
@@ -270,17 +366,22 @@ __device__ __forceinline__ void bfly_inv(u64 (&x)[16], TwRegs<LOGN, P> &t, const
 }
 
 // Forward transform of local chunk r (of 2^c).  In: x in pass-0 layout (Pass<LOGN,0>::elem), values
-// < 2q (+2q per split pre-stage); t = the pass-0 twiddles (load_tw_early<LOGN,0,false>, issued by the caller next
-// to its data loads).  Out: x in the contiguous layout (local coefficient 16*tid + j in x[j]), lazy
-// (any value < 2^64 congruent to the result: finish with reduce_full).
+// < 2q (+2q per split pre-stage) -- for Mod::dp moduli already converted with to_dp_all (load_fwd_split does) --;
+// t = the pass-0 twiddles (load_tw_early<LOGN,0,false>, issued by the caller next to its data loads).
+// Out: x in the contiguous layout (local coefficient 16*tid + j in x[j]), lazy: any value < 2^64 congruent to the
+// result, or a lazy FP64-domain value for Mod::dp moduli; canon_all finishes either.
 // Uses sm (2^LOGN words).  A CTA that runs several transforms through the same buffer passes REUSE = true: the
 // CTA-wide barrier that protects the buffer then sits right before the first store into it -- after the global loads
 // and the first pass of butterflies -- so warps leave the previous transform's elementwise tail (and enter their loads)
 // at their own pace instead of in lockstep.
-template <int LOGN, bool REUSE = false, int P = 0>
+// `hook` runs right before the butterflies of the last pass: the place from which a caller starts loads it needs
+// after the transform (k_ks_inner: the key tile), so that their latency hides behind that pass.
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <int LOGN, bool REUSE = false, int P = 0, class Hook = NoHook>
 __device__ __forceinline__ void ntt_fwd_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ tw, const Mod &m, int tid, int c, int r,
-                                                   TwRegs<LOGN, P> &t)
+                                                   TwRegs<LOGN, P> &t, Hook &&hook = Hook())
 {
+    if constexpr (P + 1 == Sched<LOGN>::NP) hook();
     bfly_fwd<LOGN, P>(x, t, m, tw, tid, (1 << c) + r);
     if constexpr (P + 1 < Sched<LOGN>::NP) {
         TwRegs<LOGN, P + 1> tn;
@@ -289,20 +390,27 @@ __device__ __forceinline__ void ntt_fwd_regs_split(u64 (&x)[16], u64 *sm, const 
         smem_xfer<LOGN, P, true>(x, sm, tid);
         xchg_sync<LOGN, P>(tid);
         smem_xfer<LOGN, P + 1, false>(x, sm, tid);
-        ntt_fwd_regs_split<LOGN, REUSE, P + 1>(x, sm, tw, m, tid, c, r, tn);
+        ntt_fwd_regs_split<LOGN, REUSE, P + 1>(x, sm, tw, m, tid, c, r, tn, hook);
     }
 }
 
 // Inverse transform of local chunk r.  In: x in the contiguous layout, canonical values (< q);
 // t = twiddles of the last pass (load_tw_early<LOGN,NP-1,true> on the inverse table).
-// Out: x in pass-0 layout; FINAL (unsplit limb): multiplied by N^{-1}, in [0,2q); otherwise lazy.
+// Out: x in pass-0 layout; FINAL (unsplit limb): multiplied by N^{-1}, in [0,2q); otherwise lazy (Mod::dp moduli:
+// FP64-domain values, to be passed through reduce_all and cross_inv).
 template <int LOGN, bool FINAL, bool REUSE = false, int P = Sched<LOGN>::NP - 1>
 __device__ __forceinline__ void ntt_inv_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ itw, const Mod &m, int tid, int c, int r,
                                                    TwRegs<LOGN, P> &t)
 {
     ulonglong2 wfold = make_ulonglong2(0, 0);
     if constexpr (FINAL && P == 0) wfold = ld_tw(itw);
+    if constexpr (P == Sched<LOGN>::NP - 1) {
+        if (m.dp) to_dp_all(x);
+    }
     bfly_inv<LOGN, P, FINAL>(x, t, m, wfold, itw, tid, (1 << c) + r);
+    if constexpr (FINAL && P == 0) {
+        if (m.dp) canon_all(x, m);   // finished values leave the FP64 domain as canonical integers
+    }
     if constexpr (P > 0) {
         TwRegs<LOGN, P - 1> tn;
         load_tw_early<LOGN, P - 1, true>(tn, itw, tid, (1 << c) + r);

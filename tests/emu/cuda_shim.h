@@ -66,6 +66,24 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 
+// ---- FP64 intrinsics used by the FP64-domain transforms (modarith.cuh); host doubles are IEEE, fma() is exact ----
+#include <fenv.h>
+#include <math.h>
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+__attribute__((noinline)) static double __fma_rd(double a, double b, double c)
+{
+    const int old = fegetround();
+    fesetround(FE_DOWNWARD);
+    volatile double va = a, vb = b, vc = c;
+    volatile double r = fma(va, vb, vc);
+    fesetround(old);
+    return r;
+}
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+
 #define B200HE_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::run_grid((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
 #define B200HE_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) \
