@@ -47,14 +47,21 @@ def peaks():
 
 
 def butterfly_peak():
-    """register-resident 64-bit Shoup butterflies per second of the whole chip, measured by tools/imad_peak.cu on
-    this pool's B200 (profiles/r1d_imad_peak.json): the integer roofline of the NTT-bearing kernels"""
-    p = os.path.join(ROOT, "profiles", "r1d_imad_peak.json")
+    """register-resident modular butterflies per second of the whole chip, measured on this pool's B200: 64-bit Shoup
+    butterflies on the integer (fma) pipe (tools/imad_peak.cu, profiles/r1d_imad_peak.json) and FP64-domain
+    butterflies of primes below 2^46 on the FP64 pipe (tools/fp64_peak.cu, profiles/r1i_fp64_peak.json): the compute
+    rooflines of the NTT-bearing kernels.  Returns (int_peak, dp_peak, source)."""
     try:
-        with open(p) as f:
-            return json.load(f)["bfly_exact_mulhi"]["Gbfly_per_s"] * 1e9, "measured (profiles/r1d_imad_peak.json)"
+        with open(os.path.join(ROOT, "profiles", "r1d_imad_peak.json")) as f:
+            ip = json.load(f)["bfly_exact_mulhi"]["Gbfly_per_s"] * 1e9
+        with open(os.path.join(ROOT, "profiles", "r1i_fp64_peak.json")) as f:
+            dp = json.load(f)["bfly_dp_45bit"]["Gbfly_per_s"] * 1e9
+        return ip, dp, "measured (profiles/r1d_imad_peak.json, profiles/r1i_fp64_peak.json)"
     except Exception:
-        return 1.0e12, "fallback (DESIGN.md §3.1)"
+        return 1.0e12, 1.93e12, "fallback (DESIGN.md §3.1)"
+
+
+DP_MAX_BITS = 46   # csrc/modarith.cuh B200HE_DP_MAX_BITS: moduli at or below run in the FP64 domain
 
 
 class ClockSampler:
@@ -154,31 +161,48 @@ def synth_inputs(moduli, n, L, N, seed):
     return out
 
 
-# butterfly-equivalents (one 64-bit Shoup multiply each) per launch of each NTT-bearing kernel class, averaged over
-# the launches of that class in one step
-def butterfly_equivalents(cls, B, L, K, N):
+# butterfly-equivalents (one modular multiply each) per launch of each NTT-bearing kernel class, averaged over the
+# launches of that class in one step, split by the pipe that executes them: returns
+# (integer-pipe butterflies, FP64-pipe butterflies).  dp[i] = modulus i of the chain runs in the FP64 domain.
+def butterfly_equivalents(cls, B, L, K, N, dp):
     bf = (N // 2) * (N.bit_length() - 1)
-    return {
-        # L(L+1) forward NTTs minus the L reused NTT-form digits, 2 inverse NTTs (special-prime limb), 2 L (L+1) N MACs
-        "k_ks_inner": (L * (L + 1) - L + 2) * bf * B + 2 * L * (L + 1) * N * B,
-        # fused relinearize+rescale mod-down of the L-1 surviving limbs: 2(L-1) NTTs + 4 Shoup scalings per coefficient
-        "k_moddown": (2 * (L - 1) * bf + 8 * (L - 1) * N) * B,
-        # two launches: the relinearization target (L limbs) and the fused last limb (2 limbs + 2 scalings per coefficient)
-        "k_ntt_inv": ((L + 2) * bf + 4 * N) * B / 2.0,
-    }.get(cls)
+    w = [0.0, 0.0]
+    if cls == "k_ks_inner":
+        # output modulus I < L: L-1 forward NTTs (the I == J digit is reused in NTT form) + 2 L N MACs;
+        # special prime: L forward + 2 inverse NTTs + 2 L N MACs
+        for I in range(L):
+            w[dp[I]] += (L - 1) * bf + 2 * L * N
+        w[dp[K - 1]] += (L + 2) * bf + 2 * L * N
+    elif cls == "k_moddown":
+        # fused relinearize+rescale mod-down of the L-1 surviving limbs: 2 NTTs per limb; the 4 Shoup scalings per
+        # coefficient and poly run on the integer pipe in either domain
+        for j in range(L - 1):
+            w[dp[j]] += 2 * bf
+            w[0] += 8 * N
+    elif cls == "k_ntt_inv":
+        # two launches: the relinearization target (one limb per data modulus) and the fused last limb (2 limbs at
+        # modulus L-1 + 2 integer scalings per coefficient); averaged per launch
+        for j in range(L):
+            w[dp[j]] += bf / 2.0
+        w[dp[L - 1]] += 2 * bf / 2.0
+        w[0] += 4 * N / 2.0
+    else:
+        return None
+    return w[0] * B, w[1] * B
 
 
 # per-launch algorithmic bytes of each kernel class for this workload (DESIGN.md "Kernels"), W = 8 B
-def algorithmic_bytes(cls, B, L, K, N):
+def algorithmic_bytes(cls, B, L, K, N, dp):
     W = 8
+    key_words = sum(1 if dp[i] else 2 for i in list(range(L)) + [K - 1])   # per coefficient, digit and component
     return {
         "k_tensor": (4 + 3) * L * N * W * B,
         # two k_ntt_inv launches per step: relinearization target (L limbs in, L out) and the fused last limb
         # (accumulator, input ciphertext and rounded special-prime limb in, rounded last limb out; 2 polys)
         "k_ntt_inv": (2 * L + 8) * N * W * B / 2.0,
         # reads target in coefficient + NTT form, writes 2L accumulator limbs and the 2 rounded special-prime limbs;
-        # key (with Shoup quotients) read once per launch
-        "k_ks_inner": (2 * L + 2 * (L + 1)) * N * W * B + 4 * L * (L + 1) * N * W,
+        # key read once per launch (16 B per coefficient with its Shoup quotient, 8 B for FP64-domain limbs)
+        "k_ks_inner": (2 * L + 2 * (L + 1)) * N * W * B + 2 * L * key_words * N * W,
         # one launch per step (fused relinearize+rescale): both rounded limbs (2 + 2), then per surviving limb and poly the
         # accumulator, the input ciphertext limb and the output
         "k_moddown": (4 + 6 * (L - 1)) * N * W * B,
@@ -347,7 +371,8 @@ def run_b200(args):
     # dominant kernel class of the step
     top = max(prof.items(), key=lambda kv: kv[1][0])
     top_name, (top_ms, top_n) = top
-    alg = algorithmic_bytes(top_name, BATCH, L, K, N)
+    dp = [1 if int(q).bit_length() <= DP_MAX_BITS and not os.environ.get("B200HE_NO_DP") else 0 for q in host.moduli]
+    alg = algorithmic_bytes(top_name, BATCH, L, K, N, dp)
     achieved = alg / (top_ms / top_n / 1e3) / 1e9 if alg else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -355,9 +380,14 @@ def run_b200(args):
         with open(tp) as f:
             traffic = json.load(f).get(top_name)
     ntt_limbs = {"k_ks_inner": L * L + 2, "k_moddown": 2 * (L - 1), "k_ntt_inv": (L + 2) / 2.0}.get(top_name, 0) * BATCH
-    bfe = butterfly_equivalents(top_name, BATCH, L, K, N)
-    bf_peak, bf_src = butterfly_peak()
-    bf_rate = bfe / (top_ms / top_n / 1e3) if bfe else None
+    bfe = butterfly_equivalents(top_name, BATCH, L, K, N, dp)
+    bf_int_peak, bf_dp_peak, bf_src = butterfly_peak()
+    # compute floor of the launch: each butterfly on its pipe at that pipe's measured register-resident rate
+    bf_rate = bf_peak = None
+    if bfe:
+        floor_s = bfe[0] / bf_int_peak + bfe[1] / bf_dp_peak
+        bf_rate = (bfe[0] + bfe[1]) / (top_ms / top_n / 1e3)
+        bf_peak = (bfe[0] + bfe[1]) / floor_s
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -371,13 +401,20 @@ def run_b200(args):
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": top_ms / top_n, "share_of_step": top_ms / (ms_total_local(prof)),
                      "limb_ntts_per_s": ntt_limbs / (top_ms / top_n / 1e3) if ntt_limbs else None,
-                     # the NTT-bearing kernels are bound by the integer (fma) pipe, not HBM: fraction of the measured
-                     # register-resident 64-bit butterfly rate of the chip
+                     # the NTT-bearing kernels are bound by the arithmetic pipes, not HBM: fraction of the measured
+                     # register-resident butterfly rate of the chip, 60-bit limbs on the integer pipe and limbs below
+                     # 2^46 on the FP64 pipe, weighted by this launch's mix
                      "int_pipe": {"achieved": bf_rate, "peak": bf_peak, "unit": "butterflies/s",
-                                  "frac": (bf_rate / bf_peak) if bf_rate else None, "peak_source": bf_src}},
+                                  "frac": (bf_rate / bf_peak) if bf_rate else None, "peak_source": bf_src,
+                                  "fp64_share_of_butterflies": (bfe[1] / (bfe[0] + bfe[1])) if bfe else None,
+                                  "int_peak": bf_int_peak, "fp64_peak": bf_dp_peak}},
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
     }
-    ntt_metric["fwd_frac_of_butterfly_peak"] = ntt_metric["fwd_butterflies_per_s"] / bf_peak
+    n_dp = sum(dp[:L])
+    ntt_peak = L / ((L - n_dp) / bf_int_peak + n_dp / bf_dp_peak)   # the transformed limbs cycle over the L data moduli
+    ntt_metric["fwd_frac_of_butterfly_peak"] = ntt_metric["fwd_butterflies_per_s"] / ntt_peak
+    ntt_metric["butterfly_peak"] = ntt_peak
+    ntt_metric["fp64_limbs"] = f"{n_dp} of {L}"
     ntt_metric["fwd_frac_of_hbm_peak"] = ntt_metric["fwd_GBps_algorithmic"] / peak
     line["ntt_limb_ops"] = ntt_metric   # per GPU
     line["cpu_baseline"] = cpu_baseline(budget_s=12.0) if world == 1 else None

@@ -92,6 +92,48 @@ def case_ntt(env, n=3):
     eq(b.download(), f.download(), "in-place forward")
 
 
+def case_extremes(env):
+    """Worst-case magnitudes for the lazy-reduction schedules of both arithmetic domains (integer pipe, and the FP64
+    domain of primes below 2^46): every residue q-1, every residue 0, alternating q-1 / 0 and q-1 / 1 patterns, with
+    an all-(q-1) relinearization key, through the transforms, relinearize and the fused relinearize+rescale"""
+    L, N = env.Ltop, env.N
+    q = env.moduli[:L].astype(np.uint64)
+    pats = []
+    for kind in range(4):
+        v = np.zeros((3, L, N), dtype=np.uint64)
+        for l in range(L):
+            if kind == 0: v[:, l, :] = q[l] - np.uint64(1)
+            elif kind == 2: v[:, l, ::2] = q[l] - np.uint64(1)
+            elif kind == 3:
+                v[:, l, ::2] = q[l] - np.uint64(1)
+                v[:, l, 1::2] = 1
+        pats.append(v)
+    x = np.stack(pats)   # [4][3][L][N]
+    b = env.ctx.batch(np.ascontiguousarray(x[:, :2]), size=2, L=L, ntt_form=False)
+    f = env.ctx.ntt_forward(b).download()
+    g = env.ctx.ntt_inverse(env.ctx.batch(np.ascontiguousarray(x[:, :2]), size=2, L=L, ntt_form=True)).download()
+    for i in range(4):
+        for l in range(L):
+            eq(f[i, 0, l], env.orc.ntt(l, x[i, 0, l]), f"extremes fwd pattern{i} limb{l}")
+            eq(g[i, 1, l], env.orc.ntt(l, x[i, 1, l], inverse=True), f"extremes inv pattern{i} limb{l}")
+    key = np.empty((L, 2, env.K, N), dtype=np.uint64)
+    for k in range(env.K):
+        key[:, :, k, :] = env.moduli[k] - np.uint64(1)
+    key = key.reshape(-1)
+    env.ctx.set_relin_key(key)
+    try:
+        X = env.batch(x, size=3, L=L, scale=2.0 ** 80)
+        got = env.ctx.relinearize(X).download()
+        for i in range(4):
+            eq(got[i], env.orc.relinearize(L, x[i].reshape(-1), key), f"extremes relinearize pattern{i}")
+        if env.scheme == CKKS and L >= 2:
+            got = env.ctx.relinearize_rescale(X).download()
+            for i in range(4):
+                eq(got[i], env.orc.rescale(L, 2, env.orc.relinearize(L, x[i].reshape(-1), key)), f"extremes fused pattern{i}")
+    finally:
+        env.ctx.set_relin_key(env.relin)
+
+
 def case_elementwise(env, n0=3, n1=2):
     """K3/K4: add, sub, CKKS multiply over the reference's b0 x b1 result grid (index maps)"""
     L = env.Ltop

@@ -9,6 +9,8 @@ from helpers import BFV, CKKS
 CKKS_CHAINS = {
     "N1024-3": (1024, [60, 40, 60]),
     "N2048-4": (2048, [60, 45, 45, 60]),
+    # FP64-domain boundary: 46-bit primes run on the FP64 pipe, 47-bit ones on the integer pipe (modarith.cuh)
+    "N1024-dp-edge": (1024, [47, 46, 30, 46, 60]),
 }
 
 
@@ -30,6 +32,10 @@ def bfv(emu_lib):
 
 def test_ntt(ckks):
     parity.case_ntt(ckks)
+
+
+def test_extremes(ckks):
+    parity.case_extremes(ckks)
 
 
 def test_elementwise(ckks):
@@ -110,6 +116,9 @@ def test_split_limb(emu_lib):
         parity.case_rescale(env, n=1, sizes=(2,))
         parity.case_relin_rescale_fused(env, n=1)
         env.close()
+    env = parity.Env(emu_lib, CKKS, 16384, [46, 47, 46, 60], galois_steps=(1,))
+    parity.case_extremes(env)
+    env.close()
 
 
 def test_decrypt_level(emu_lib):

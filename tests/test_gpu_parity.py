@@ -16,6 +16,8 @@ CKKS_CHAINS = {
     "C4-N16384-K7": (16384, [60, 45, 45, 45, 45, 45, 60]),
     "C5-N32768-K7": (32768, [60, 45, 45, 45, 45, 45, 60]),
     "small-N4096-K4": (4096, [60, 40, 40, 60]),
+    # FP64-domain boundary: 46-bit primes run on the FP64 pipe, 47-bit ones on the integer pipe (modarith.cuh)
+    "dp-edge-N16384-K5": (16384, [47, 46, 30, 46, 60]),
 }
 
 
@@ -42,6 +44,10 @@ def test_loaded_library_is_cuda(gpu_lib):
 
 def test_ntt(ckks):
     parity.case_ntt(ckks, n=2)
+
+
+def test_extremes(ckks):
+    parity.case_extremes(ckks)
 
 
 def test_elementwise(ckks):
