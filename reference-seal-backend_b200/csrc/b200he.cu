@@ -225,6 +225,14 @@ static Mod make_mod(u64 q, u64 N)
     m.r64 = (u64)((((hm::u128)1) << 64) / q);
     m.ninv = hm::invmod(N % q, q);
     m.ninv_s = hm::shoup(m.ninv, q);
+    // pseudo-Mersenne lazy reduction (modarith.cuh reduce_pm): q = 2^bits - c with (2^(64-bits) - 1) c + 2^bits - 1 < 2q
+    {
+        const hm::u128 c = ((hm::u128)1 << m.bits) - q;
+        static const bool no_pm = getenv("B200HE_NO_PM") && atoi(getenv("B200HE_NO_PM"));
+        if (!no_pm && m.bits > 32 && c < ((hm::u128)1 << 32) &&
+            (((hm::u128)1 << (64 - m.bits)) - 1) * c + (((hm::u128)1 << m.bits) - 1) < (hm::u128)2 * q)
+            m.pm_c = (u32)c;
+    }
     // FP64 domain for small primes (modarith.cuh); B200HE_NO_DP=1 keeps every modulus on the integer pipe (A/B timing)
     static const bool no_dp = getenv("B200HE_NO_DP") && atoi(getenv("B200HE_NO_DP"));
     m.dp = (m.bits <= B200HE_DP_MAX_BITS && !no_dp) ? 1 : 0;

@@ -40,6 +40,8 @@ struct Mod {
     u32 inv_c[4];   // inverse: bound multiplier C (values < C*q) at the start of pass P
     u32 acc_period; // key-switch inner product: reduce the lazy accumulators every acc_period digits
     u32 dp;         // 1: the transforms of this modulus run in the FP64 domain (q < 2^DP_MAX_BITS, see below)
+    u32 pm_c;       // q = 2^bits - pm_c with pm_c small enough for reduce_pm (0: not of that form)
+    u32 pad_;
     double dq, dnq, dqinv, dqinv_up;   // q, -q, RN(1/q), 1/q rounded up
     double dninv, dninv_q;             // N^{-1} mod q and RN(N^{-1}/q)
 };
@@ -75,6 +77,13 @@ __host__ __device__ __forceinline__ u64 shoup_mad(u64 y, u64 w, u64 ws, u64 nq, 
 }
 // any 64-bit x -> x mod q + {0,q}  (in [0,2q)).  NARROW: floor(2^64/q) fits 32 bits (q > 2^32), then
 // the quotient costs 2 multiply-adds instead of 4.  Callers branch once per CTA on Mod::bits.
+// q = 2^b - c (every prime SEAL's CoeffModulus::Create picks is the largest few below a power of two, c ~ 2^14..2^22):
+// x = xh 2^b + xl = xl + xh c (mod q), one shift, one mask and one IMAD.WIDE instead of the 3 wide products of the
+// Barrett quotient.  The host sets Mod::pm_c only when (2^(64-b) - 1) c + 2^b - 1 < 2q, so the result is in [0, 2q).
+__host__ __device__ __forceinline__ u64 reduce_pm(u64 x, u32 b, u32 c)
+{
+    return (x & ((u64(1) << b) - 1)) + (u64)(u32)(x >> b) * c;
+}
 template <bool NARROW> __host__ __device__ __forceinline__ u64 reduce_lazy_t(u64 x, const Mod &m)
 {
     if (NARROW) {
@@ -85,7 +94,11 @@ template <bool NARROW> __host__ __device__ __forceinline__ u64 reduce_lazy_t(u64
     }
     return x + mulhi64(x, m.r64) * m.nq;
 }
-__host__ __device__ __forceinline__ u64 reduce_lazy(u64 x, const Mod &m) { return m.bits > 32 ? reduce_lazy_t<true>(x, m) : reduce_lazy_t<false>(x, m); }
+__host__ __device__ __forceinline__ u64 reduce_lazy(u64 x, const Mod &m)
+{
+    if (m.pm_c) return reduce_pm(x, m.bits, m.pm_c);
+    return m.bits > 32 ? reduce_lazy_t<true>(x, m) : reduce_lazy_t<false>(x, m);
+}
 // any 64-bit x -> canonical x mod q
 __host__ __device__ __forceinline__ u64 reduce_full(u64 x, const Mod &m) { return csub(reduce_lazy(x, m), m.q); }
 

@@ -173,6 +173,12 @@ __device__ __forceinline__ void reduce_all(u64 (&x)[16], const Mod &m)
         for (int i = 0; i < 16; i++) x[i] = as_u(dp_reduce(as_d(x[i]), m.dqinv, m.dnq));
         return;
     }
+    if (m.pm_c) {
+        const u32 b = m.bits, c = m.pm_c;
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = reduce_pm(x[i], b, c);
+        return;
+    }
     if (m.bits > 32) {
 #pragma unroll
         for (int i = 0; i < 16; i++) x[i] = reduce_lazy_t<true>(x[i], m);
