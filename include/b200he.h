@@ -71,6 +71,14 @@ int b200he_batch_upload(b200he_batch *b, uint64_t first, uint64_t n, const uint6
 int b200he_batch_download(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host);
 /* same without the wait: `host` (pinned memory) is valid after the next b200he_ctx_sync */
 int b200he_batch_download_async(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host);
+/* The whole of BaseBenchmark::load / store for a parameter: n separately allocated pageable host ciphertexts
+ * (host[i] = seal::Ciphertext::data() of ciphertext first+i, ct_words each; R/src/benchmarks/ckks/
+ * seal_ckks_dot_product_benchmark.cpp:267-291) <-> ciphertexts [first, first+n) of the batch.  Staged through the
+ * context's double-buffered pinned memory: host threads gather/scatter one chunk while the copy engine moves the
+ * other.  upload returns once every host[i] has been read (the last H2D copy may still be in flight on the context's
+ * stream); download returns when every host[i] is complete. */
+int b200he_batch_upload_scattered(b200he_batch *b, uint64_t first, uint64_t n, const uint64_t *const *host);
+int b200he_batch_download_scattered(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *const *host);
 uint64_t b200he_batch_count(const b200he_batch *b);
 int b200he_batch_size(const b200he_batch *b);
 int b200he_batch_level(const b200he_batch *b);      /* L = number of RNS limbs */

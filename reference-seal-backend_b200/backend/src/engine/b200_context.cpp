@@ -182,13 +182,16 @@ DeviceBatchPtr SEALContextWrapper::upload(int g, const std::vector<Ciphertext> &
     }
     const Ciphertext &c0 = src[first];
     check(b200he_batch_resize(b->get(), n, c0.size, c0.L, c0.ntt, c0.scale), "b200he_batch_resize");
+    // one call for the whole range: the library gathers the separately allocated ciphertexts into pinned staging
+    // buffers on a few host threads while the previous chunk crosses PCIe, and returns once every source has been read
+    std::vector<const std::uint64_t *> ptrs(n);
     for (std::size_t i = 0; i < n; ++i) {
         const Ciphertext &c = src[first + i];
         if (c.size != c0.size || c.L != c0.L || c.ntt != c0.ntt)
             throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("ciphertexts of one batch must share size, level and form"), HEBENCH_ECODE_INVALID_ARGS);
-        check(b200he_batch_upload(b->get(), i, 1, c.data.data()), "b200he_batch_upload");
+        ptrs[i] = c.data.data();
     }
-    check(b200he_ctx_sync(m_dev[g]), "b200he_ctx_sync");   // host vectors may go away
+    check(b200he_batch_upload_scattered(b->get(), 0, n, ptrs.data()), "b200he_batch_upload_scattered");
     return b;
 }
 DeviceBatchPtr SEALContextWrapper::upload(int g, const Ciphertext &src) const
@@ -201,23 +204,33 @@ DeviceBatchPtr SEALContextWrapper::uploadPlain(int g, const std::vector<Plaintex
     DeviceBatchPtr b = newBatch(g);
     if (src.empty()) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("empty plaintext batch"), HEBENCH_ECODE_INVALID_ARGS);
     check(b200he_batch_resize(b->get(), src.size(), 1, src[0].L, 1, src[0].scale), "b200he_batch_resize");
-    for (std::size_t i = 0; i < src.size(); ++i) check(b200he_batch_upload(b->get(), i, 1, src[i].data.data()), "b200he_batch_upload");
-    check(b200he_ctx_sync(m_dev[g]), "b200he_ctx_sync");
+    std::vector<const std::uint64_t *> ptrs(src.size());
+    for (std::size_t i = 0; i < src.size(); ++i) {
+        if (src[i].L != src[0].L) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("plaintexts of one batch must share the level"), HEBENCH_ECODE_INVALID_ARGS);
+        ptrs[i] = src[i].data.data();
+    }
+    check(b200he_batch_upload_scattered(b->get(), 0, src.size(), ptrs.data()), "b200he_batch_upload_scattered");
     return b;
 }
 std::vector<Ciphertext> SEALContextWrapper::download(const DeviceBatch &b) const
 {
     std::vector<Ciphertext> out(b.count());
     const std::size_t words = (std::size_t)b.size() * b.level() * m_N;
+    std::vector<std::uint64_t *> ptrs(out.size());
+    const bool ntt = b200he_batch_ntt_form(b.get()) != 0;
+    // first touch of the result vectors on all host threads (page faults dominate a fresh 0.4-3 MB vector), then one
+    // staged download for the whole batch
+#pragma omp parallel for schedule(static)
     for (std::size_t i = 0; i < out.size(); ++i) {
         Ciphertext &c = out[i];
         c.size        = b.size();
         c.L           = b.level();
-        c.ntt         = b200he_batch_ntt_form(b.get()) != 0;
+        c.ntt         = ntt;
         c.scale       = b.scale();
         c.data.resize(words);
-        check(b200he_batch_download(b.get(), i, 1, c.data.data()), "b200he_batch_download");
+        ptrs[i] = c.data.data();
     }
+    check(b200he_batch_download_scattered(b.get(), 0, out.size(), ptrs.data()), "b200he_batch_download_scattered");
     return out;
 }
 void SEALContextWrapper::syncAll() const

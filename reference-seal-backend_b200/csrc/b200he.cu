@@ -16,6 +16,7 @@
 
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hostmath.h"
@@ -148,6 +149,11 @@ struct b200he_ctx {
     std::vector<ProfRec> recs;
     Behz behz{};   // BFV only
     int nBsk = 0;
+    // pinned staging of b200he_batch_{upload,download}_scattered: two buffers, each guarded by the event of the last
+    // copy that used it
+    void *stage_buf[2] = { nullptr, nullptr };
+    cudaEvent_t stage_ev[2] = { nullptr, nullptr };
+    size_t stage_bytes = 0;
 };
 
 struct b200he_batch {
@@ -355,6 +361,7 @@ template <int LG, int CC> static int set_smem_attrs()
 }
 
 static int init_behz(b200he_ctx *c, std::vector<u64> &moduli, std::vector<u64> &psi);
+static int stage_init(b200he_ctx *c, size_t ct_bytes);
 static int upload_behz(b200he_ctx *c);
 
 extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint64_t *moduli, const uint64_t *psi,
@@ -405,6 +412,8 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
     int rc = 0;
     KERNEL_DISPATCH(c, (rc = set_smem_attrs<LG, CC>()));
     if (rc) { delete c; return rc; }
+    // pinned staging for load()/store() (page-locking 64 MB takes tens of milliseconds: not inside the first load)
+    if (stage_init(c, 0)) { delete c; return -1; }
     // the tables were uploaded with synchronous copies from pageable memory (NULL stream): make sure they have landed
     // before the first kernel on the context's non-blocking stream can run
     if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return fail("ctx_create: device synchronisation failed"); }
@@ -425,6 +434,10 @@ extern "C" void b200he_ctx_destroy(b200he_ctx *c)
     for (auto &kv : c->pool.sizes) cudaFree(kv.first);   // blocks still held by undestroyed batches
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->behz.d_blob) cudaFree(c->behz.d_blob);
+    for (int i = 0; i < 2; i++) {
+        if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
 #ifndef B200HE_EMU
     if (c->own_stream) cudaStreamDestroy(c->stream);
 #endif
@@ -595,6 +608,96 @@ extern "C" int b200he_batch_download_async(const b200he_batch *b, uint64_t first
     if (first + n > b->count) return fail("batch_download_async: range exceeds count");
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaMemcpyAsync(host, b->d + first * b->ct_words(), n * b->ct_words() * 8, cudaMemcpyDeviceToHost, b->ctx->stream));
+    return 0;
+}
+// ---- load / store of separately allocated host ciphertexts through pinned staging ----
+static int stage_init(b200he_ctx *c, size_t ct_bytes)
+{
+    size_t want = size_t(32) << 20;
+    if (const char *e = getenv("B200HE_STAGE_MB")) want = (size_t)atoi(e) << 20;
+    if (want < ct_bytes) want = ct_bytes;
+    if (c->stage_bytes >= want) return 0;
+    for (int i = 0; i < 2; i++) {
+        if (c->stage_ev[i]) CK(cudaEventSynchronize(c->stage_ev[i]));
+        if (c->stage_buf[i]) CK(cudaFreeHost(c->stage_buf[i]));
+        c->stage_buf[i] = nullptr;
+        CK(cudaMallocHost(&c->stage_buf[i], want));
+        if (!c->stage_ev[i]) CK(cudaEventCreate(&c->stage_ev[i]));
+    }
+    c->stage_bytes = want;
+    return 0;
+}
+// run fn(i) for i in [0, n) on a few host threads (the copies are memory-bound: a handful of cores saturate DRAM)
+template <class F> static void host_parallel(size_t n, F fn)
+{
+    size_t T = std::thread::hardware_concurrency();
+    if (const char *e = getenv("B200HE_HOST_THREADS")) T = (size_t)atoi(e);
+    if (T > 8) T = 8;
+    if (T > n) T = n;
+    if (T <= 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < T; t++)
+        th.emplace_back([=]() {
+            for (size_t i = t; i < n; i += T) fn(i);
+        });
+    for (auto &x : th) x.join();
+}
+extern "C" int b200he_batch_upload_scattered(b200he_batch *b, uint64_t first, uint64_t n, const uint64_t *const *host)
+{
+    if (!b || (!host && n)) return fail("batch_upload_scattered: NULL argument");
+    if (first + n > b->count) return fail("batch_upload_scattered: range exceeds count");
+    if (!n) return 0;
+    for (uint64_t i = 0; i < n; i++)
+        if (!host[i]) return fail("batch_upload_scattered: host[%llu] is NULL", (unsigned long long)i);
+    b200he_ctx *c = b->ctx;
+    CK(cudaSetDevice(c->device));
+    const size_t ctb = b->ct_words() * 8;
+    TRY(stage_init(c, ctb));
+    const uint64_t per = c->stage_bytes / ctb;
+    int k = 0;
+    for (uint64_t at = 0; at < n; at += per, k ^= 1) {
+        const uint64_t m = n - at < per ? n - at : per;
+        CK(cudaEventSynchronize(c->stage_ev[k]));   // the copy that last used this buffer has finished
+        unsigned char *buf = (unsigned char *)c->stage_buf[k];
+        host_parallel(m, [&](size_t i) { memcpy(buf + i * ctb, host[at + i], ctb); });
+        CK(cudaMemcpyAsync(b->d + (first + at) * b->ct_words(), buf, m * ctb, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->stage_ev[k], c->stream));
+    }
+    return 0;
+}
+extern "C" int b200he_batch_download_scattered(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *const *host)
+{
+    if (!b || (!host && n)) return fail("batch_download_scattered: NULL argument");
+    if (first + n > b->count) return fail("batch_download_scattered: range exceeds count");
+    if (!n) return 0;
+    for (uint64_t i = 0; i < n; i++)
+        if (!host[i]) return fail("batch_download_scattered: host[%llu] is NULL", (unsigned long long)i);
+    b200he_ctx *c = b->ctx;
+    CK(cudaSetDevice(c->device));
+    const size_t ctb = b->ct_words() * 8;
+    TRY(stage_init(c, ctb));
+    const uint64_t per = c->stage_bytes / ctb;
+    // chunk j+1 moves over PCIe while the host threads scatter chunk j
+    auto issue = [&](uint64_t at, int k) -> int {
+        const uint64_t m = n - at < per ? n - at : per;
+        CK(cudaEventSynchronize(c->stage_ev[k]));
+        CK(cudaMemcpyAsync(c->stage_buf[k], b->d + (first + at) * b->ct_words(), m * ctb, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaEventRecord(c->stage_ev[k], c->stream));
+        return 0;
+    };
+    TRY(issue(0, 0));
+    int k = 0;
+    for (uint64_t at = 0; at < n; at += per, k ^= 1) {
+        const uint64_t m = n - at < per ? n - at : per;
+        if (at + per < n) TRY(issue(at + per, k ^ 1));
+        CK(cudaEventSynchronize(c->stage_ev[k]));
+        const unsigned char *buf = (const unsigned char *)c->stage_buf[k];
+        host_parallel(m, [&](size_t i) { memcpy(host[at + i], buf + i * ctb, ctb); });
+    }
+    CK(cudaGetLastError());
     return 0;
 }
 extern "C" uint64_t b200he_batch_count(const b200he_batch *b) { return b ? b->count : 0; }

@@ -37,6 +37,8 @@ SIGNATURES = {
     "b200he_batch_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_batch_download": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_batch_download_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b200he_batch_upload_scattered": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b200he_batch_download_scattered": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_batch_count": (C.c_uint64, [C.c_void_p]),
     "b200he_batch_size": (C.c_int, [C.c_void_p]),
     "b200he_batch_level": (C.c_int, [C.c_void_p]),
@@ -156,6 +158,20 @@ class Batch:
     def download_to(self, ptr, first, n, wait=True):
         fn = self.lib.b200he_batch_download if wait else self.lib.b200he_batch_download_async
         self.ctx._ck(fn(self.h, first, n, ptr))
+
+    def upload_scattered(self, arrays, first=0):
+        """load(): separately allocated host ciphertexts (one contiguous uint64 array each) -> ciphertexts
+        [first, first+len) of the batch, through the context's pinned staging"""
+        ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        self.ctx._ck(self.lib.b200he_batch_upload_scattered(self.h, first, len(arrays), ptrs))
+
+    def download_scattered(self, first=0, n=None):
+        """store(): ciphertexts [first, first+n) -> n separately allocated host arrays"""
+        n = self.count - first if n is None else n
+        outs = [np.empty((self.size, self.L, self.ctx.N), dtype=np.uint64) for _ in range(n)]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in outs])
+        self.ctx._ck(self.lib.b200he_batch_download_scattered(self.h, first, n, ptrs))
+        return outs
 
     def download(self, first=0, n=None):
         n = self.count - first if n is None else n

@@ -4,6 +4,6 @@
 set -e
 here=$(cd "$(dirname "$0")" && pwd)
 root=$(cd "$here/../.." && pwd)
-g++ -O2 -ffp-contract=off -std=c++17 -fPIC -shared -DB200HE_EMU -x c++ -I"$root/tests" -I"$root/reference-seal-backend_b200/csrc" \
+g++ -O2 -pthread -ffp-contract=off -std=c++17 -fPIC -shared -DB200HE_EMU -x c++ -I"$root/tests" -I"$root/reference-seal-backend_b200/csrc" \
     -Wno-unknown-pragmas -o "$here/libb200he_emu.so" \
     "$root/reference-seal-backend_b200/csrc/b200he.cu" "$here/cuda_shim.cpp"

@@ -92,6 +92,26 @@ def case_ntt(env, n=3):
     eq(b.download(), f.download(), "in-place forward")
 
 
+def case_scattered(env, n=7):
+    """load()/store() of separately allocated host ciphertexts through the pinned staging buffers
+    (b200he_batch_{upload,download}_scattered): round trip, sub-ranges, and agreement with the contiguous calls"""
+    x = env.rand_ct(n, size=2)
+    parts = [np.ascontiguousarray(x[i]) for i in range(n)]
+    b = env.ctx.batch(np.zeros_like(x), size=2, L=env.Ltop)
+    b.upload_scattered(parts)
+    eq(b.download(), x, "scattered upload vs contiguous download")
+    outs = b.download_scattered()
+    for i in range(n):
+        eq(outs[i], x[i], f"scattered download ct{i}")
+    b.upload_scattered(parts[:2], first=n - 2)   # sub-range
+    eq(b.download(n - 2, 2), x[:2], "scattered upload into a sub-range")
+    outs = b.download_scattered(1, 3)
+    for i in range(3):
+        eq(outs[i], x[1 + i], f"scattered download sub-range ct{i}")
+    b.upload_scattered([])
+    assert b.download_scattered(0, 0) == []
+
+
 def case_extremes(env):
     """Worst-case magnitudes for the lazy-reduction schedules of both arithmetic domains (integer pipe, and the FP64
     domain of primes below 2^46): every residue q-1, every residue 0, alternating q-1 / 0 and q-1 / 1 patterns, with

@@ -50,6 +50,10 @@ def test_extremes(ckks):
     parity.case_extremes(ckks)
 
 
+def test_scattered_load_store(ckks, monkeypatch):
+    parity.case_scattered(ckks)
+
+
 def test_elementwise(ckks):
     parity.case_elementwise(ckks)
 
