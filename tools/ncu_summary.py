@@ -16,6 +16,7 @@ KEYS = [
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
     ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy%"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "alu%"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", "fp64%"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
     ("smsp__inst_executed.sum", "warp_insts"),
