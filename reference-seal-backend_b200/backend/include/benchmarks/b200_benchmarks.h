@@ -151,7 +151,16 @@ public:
     enum : std::size_t { Index_W = 0, Index_b, Index_X };
     // (0.5 + 0.15012 x - 0.0015930078125 x^3), R/include/benchmarks/ckks/seal_ckks_logreg_horner.h
     static constexpr double SigmoidPolyCoeff[] = { 0.5, 0.15012, 0.0, -0.0015930078125 };
-    LogRegHornerBenchmarkDescription(hebench::APIBridge::Category category, std::size_t batch_size = 0);
+    // The api-bridge also defines LogisticRegression_PolyD5 / _PolyD7 (BASELINE.json configs[4]); the reference
+    // registers only D3.  Degree 5 and 7 use the least-squares sigmoid polynomials of the same family
+    // (g5(x) = 0.5 + 1.53048 (x/8) - 2.3533056 (x/8)^3 + 1.3511295 (x/8)^5,
+    //  g7(x) = 0.5 + 1.73496 (x/8) - 4.19407 (x/8)^3 + 5.43402 (x/8)^5 - 2.50739 (x/8)^7), same Horner evaluation.
+    static constexpr double SigmoidPolyCoeffD5[] = { 0.5, 0.19131, 0.0, -0.0045963, 0.0, 0.0000412332 };
+    static constexpr double SigmoidPolyCoeffD7[] = { 0.5, 0.21687, 0.0, -0.0081918, 0.0, 0.000165838, 0.0, -0.00000119581 };
+    static std::vector<double> sigmoidCoefficients(hebench::APIBridge::Workload w);
+    static std::size_t polynomialDegree(hebench::APIBridge::Workload w);
+    LogRegHornerBenchmarkDescription(hebench::APIBridge::Category category, std::size_t batch_size = 0,
+                                     hebench::APIBridge::Workload workload = hebench::APIBridge::Workload::LogisticRegression_PolyD3);
     hebench::cpp::BaseBenchmark *createBenchmark(hebench::cpp::BaseEngine &engine, const hebench::APIBridge::WorkloadParams *p_params) override;
 };
 

@@ -1,4 +1,4 @@
-// b200_logreg_benchmark.cpp -- CKKS logistic-regression inference with a degree-3 sigmoid (Horner).
+// b200_logreg_benchmark.cpp -- CKKS logistic-regression inference with a degree-3 (reference) / 5 / 7 sigmoid (Horner).
 // Replaces R/src/benchmarks/ckks/seal_ckks_logreg_horner.cpp.  operate() keeps the reference's op sequence:
 //   per sample:  multiply(W, X_i) -> relinearize -> accumulateCKKS(n) -> rescale        (…logreg_horner.cpp:425-444)
 //   collapse:    rotate sample i by -i, mask, rescale, sum                               (R/src/engine/seal_context.cpp:349-415)
@@ -22,12 +22,36 @@ using hebench::APIBridge::Workload;
 using hebench::cpp::HEBenchError;
 
 constexpr double LogRegHornerBenchmarkDescription::SigmoidPolyCoeff[];
+constexpr double LogRegHornerBenchmarkDescription::SigmoidPolyCoeffD5[];
+constexpr double LogRegHornerBenchmarkDescription::SigmoidPolyCoeffD7[];
 
-LogRegHornerBenchmarkDescription::LogRegHornerBenchmarkDescription(Category category, std::size_t batch_size)
+std::size_t LogRegHornerBenchmarkDescription::polynomialDegree(Workload w)
 {
-    // R/include/benchmarks/ckks/seal_ckks_logreg_horner.h:57-61: N = 16384, {60, 45 x 5, 60}
-    setup(true, Workload::LogisticRegression_PolyD3, category, 1 /* LogRegOtherID */, AlgorithmName, AlgorithmDescription, { 16 }, { "n" },
-          EncryptionParams{ 16384, 6, 45, 45, 0 });
+    switch (w) {
+    case Workload::LogisticRegression_PolyD3: return 3;
+    case Workload::LogisticRegression_PolyD5: return 5;
+    case Workload::LogisticRegression_PolyD7: return 7;
+    default: return 0;
+    }
+}
+std::vector<double> LogRegHornerBenchmarkDescription::sigmoidCoefficients(Workload w)
+{
+    switch (polynomialDegree(w)) {
+    case 3: return std::vector<double>(SigmoidPolyCoeff, SigmoidPolyCoeff + 4);
+    case 5: return std::vector<double>(SigmoidPolyCoeffD5, SigmoidPolyCoeffD5 + 6);
+    case 7: return std::vector<double>(SigmoidPolyCoeffD7, SigmoidPolyCoeffD7 + 8);
+    default: return {};
+    }
+}
+
+LogRegHornerBenchmarkDescription::LogRegHornerBenchmarkDescription(Category category, std::size_t batch_size, Workload workload)
+{
+    // R/include/benchmarks/ckks/seal_ckks_logreg_horner.h:57-61: N = 16384, {60, 45 x 5, 60} for degree 3.
+    // One level for W.X, one for the collapse mask, one per Horner step, one to spare: 6 / 8 / 10; the deeper chains
+    // ({60, 45 x 9, 60} = 525 bits for degree 7) need N = 32768 at 128-bit security.
+    const std::size_t degree = polynomialDegree(workload);
+    setup(true, workload, category, 1 /* LogRegOtherID */, AlgorithmName, AlgorithmDescription, { 16 }, { "n" },
+          EncryptionParams{ degree > 3 ? 32768u : 16384u, (std::uint64_t)(degree + 3), 45, 45, 0 });
     if (category == Category::Offline) {   // W and b: one sample each; X: the batch (0 = chosen by the harness)
         m_descriptor.cat_params.offline.data_count[Index_W] = 1;
         m_descriptor.cat_params.offline.data_count[Index_b] = 1;
@@ -47,23 +71,23 @@ LogRegHornerBenchmark::LogRegHornerBenchmark(hebench::cpp::BaseEngine &engine, c
     : hebench::cpp::BaseBenchmark(engine, bench_desc, bench_params), m_w_params(bench_params)
 {
     const hebench::APIBridge::BenchmarkDescriptor &d = getDescriptor();
-    if (d.workload != Workload::LogisticRegression_PolyD3 || d.data_type != hebench::APIBridge::DataType::Float64
+    const std::size_t degree = LogRegHornerBenchmarkDescription::polynomialDegree(d.workload);
+    if (degree == 0 || d.data_type != hebench::APIBridge::DataType::Float64
         || (d.cipher_param_mask & 0x03) != 0x03 || d.scheme != HEBENCH_HE_SCHEME_CKKS || d.security != HEBENCH_HE_SECURITY_128)
         throw HEBenchError(HEBERROR_MSG_CLASS("Benchmark descriptor received is not supported."), HEBENCH_ECODE_INVALID_ARGS);
     if (d.category == Category::Offline && (d.cat_params.offline.data_count[0] > 1 || d.cat_params.offline.data_count[1] > 1))
         throw HEBenchError(HEBERROR_MSG_CLASS("Benchmark descriptor received is not supported."), HEBENCH_ECODE_INVALID_ARGS);
     if (ep.coeff_modulus_bits < 1) throw HEBenchError(HEBERROR_MSG_CLASS("Multiplicative depth must be greater than 0."), HEBENCH_ECODE_INVALID_ARGS);
-    // one level for W.X, one for the collapse mask, three for the degree-3 Horner evaluation
-    if (ep.multiplicative_depth < 6)
-        throw HEBenchError(HEBERROR_MSG_CLASS("Multiplicative depth must be at least 6 for this workload."), HEBENCH_ECODE_INVALID_ARGS);
+    // one level for W.X, one for the collapse mask, one per Horner step (degree 3: 6 as in the reference, :110)
+    if (ep.multiplicative_depth < degree + 3)
+        throw HEBenchError(HEBERROR_MSG_CLASS("Multiplicative depth must be at least " + std::to_string(degree + 3) + " for this workload."), HEBENCH_ECODE_INVALID_ARGS);
     m_p_ctx_wrapper = makeContext(true, ep);
     if (m_w_params.n() > m_p_ctx_wrapper->slotCount())
         throw HEBenchError(HEBERROR_MSG_CLASS("Invalid workload parameter 'n'. Number of features must be under " + std::to_string(m_p_ctx_wrapper->slotCount()) + "."),
                            HEBENCH_ECODE_INVALID_ARGS);
     // sigmoid coefficients, each broadcast to every slot
-    const std::size_t n_coeff = sizeof(LogRegHornerBenchmarkDescription::SigmoidPolyCoeff) / sizeof(double);
-    for (std::size_t i = 0; i < n_coeff; ++i)
-        m_plain_coeff.push_back(m_p_ctx_wrapper->encodeVector(std::vector<double>(m_p_ctx_wrapper->slotCount(), LogRegHornerBenchmarkDescription::SigmoidPolyCoeff[i])));
+    for (double coeff : LogRegHornerBenchmarkDescription::sigmoidCoefficients(d.workload))
+        m_plain_coeff.push_back(m_p_ctx_wrapper->encodeVector(std::vector<double>(m_p_ctx_wrapper->slotCount(), coeff)));
 }
 
 Handle LogRegHornerBenchmark::encode(const DataPackCollection *p_parameters)

@@ -67,4 +67,10 @@ void SEALEngine::init()
     addBenchmarkDescription(std::make_shared<sbe::ckks::MatMultRowBenchmarkDescription>());
     addBenchmarkDescription(std::make_shared<sbe::ckks::LogRegHornerBenchmarkDescription>(Category::Latency));
     addBenchmarkDescription(std::make_shared<sbe::ckks::LogRegHornerBenchmarkDescription>(Category::Offline, 0));
+    // beyond the reference's 20 (kept last so the reference's indices are unchanged): the api-bridge's degree-5 and
+    // degree-7 logistic-regression workloads (BASELINE.json configs[4]), same Horner benchmark class
+    for (hebench::APIBridge::Workload w : { hebench::APIBridge::Workload::LogisticRegression_PolyD5, hebench::APIBridge::Workload::LogisticRegression_PolyD7 }) {
+        addBenchmarkDescription(std::make_shared<sbe::ckks::LogRegHornerBenchmarkDescription>(Category::Latency, 0, w));
+        addBenchmarkDescription(std::make_shared<sbe::ckks::LogRegHornerBenchmarkDescription>(Category::Offline, 0, w));
+    }
 }

@@ -42,8 +42,20 @@ static const char *workloadName(Workload w)
     case DotProduct: return "DotProduct";
     case MatrixMultiply: return "MatrixMultiply";
     case LogisticRegression_PolyD3: return "LogisticRegression_PolyD3";
+    case LogisticRegression_PolyD5: return "LogisticRegression_PolyD5";
+    case LogisticRegression_PolyD7: return "LogisticRegression_PolyD7";
     default: return "Other";
     }
+}
+
+static bool is_logreg(Workload w) { return w == LogisticRegression_PolyD3 || w == LogisticRegression_PolyD5 || w == LogisticRegression_PolyD7; }
+// ground truth of the sigmoid approximations (HEBench's logistic-regression workloads, degree 3 / 5 / 7)
+static double sigmoid_poly(Workload w, double x)
+{
+    const double x2 = x * x;
+    if (w == LogisticRegression_PolyD5) return 0.5 + x * (0.19131 + x2 * (-0.0045963 + x2 * 0.0000412332));
+    if (w == LogisticRegression_PolyD7) return 0.5 + x * (0.21687 + x2 * (-0.0081918 + x2 * (0.000165838 + x2 * -0.00000119581)));
+    return 0.5 + 0.15012 * x - 0.0015930078125 * x * x * x;
 }
 
 struct NativeData {   // owns the buffers of a DataPackCollection
@@ -150,7 +162,7 @@ int main(int argc, char **argv)
         // concrete sample counts
         uint64_t s0 = 1, s1 = 1, batch = 1;
         if (bd.category == Offline) {
-            if (bd.workload == LogisticRegression_PolyD3) { batch = o.batch; bd.cat_params.offline.data_count[2] = batch; }
+            if (is_logreg(bd.workload)) { batch = o.batch; bd.cat_params.offline.data_count[2] = batch; }
             else { s0 = o.samples[0]; s1 = o.samples[1]; bd.cat_params.offline.data_count[0] = s0; bd.cat_params.offline.data_count[1] = s1; }
         }
         printf("[ Info    ] %2lu: %s:", bi, title.str().c_str());
@@ -165,7 +177,7 @@ int main(int argc, char **argv)
             continue;
         }
         // ---- inputs + ground truth
-        std::uniform_real_distribution<double> ud(bd.workload == LogisticRegression_PolyD3 ? -0.5 : -1.0, bd.workload == LogisticRegression_PolyD3 ? 0.5 : 1.0);
+        std::uniform_real_distribution<double> ud(is_logreg(bd.workload) ? -0.5 : -1.0, is_logreg(bd.workload) ? 0.5 : 1.0);
         std::uniform_int_distribution<int64_t> id(-10, 10);
         auto fill = [&](std::vector<unsigned char> &buf, size_t n) {
             buf.resize(n * 8);
@@ -226,7 +238,7 @@ int main(int argc, char **argv)
             for (uint64_t s = 0; s < batch; ++s) {
                 double x = val(in.bytes[1][0], 0);
                 for (uint64_t k = 0; k < n; ++k) x += val(in.bytes[0][0], k) * val(in.bytes[2][s], k);
-                truth.push_back({ 0.5 + 0.15012 * x - 0.0015930078125 * x * x * x });
+                truth.push_back({ sigmoid_poly(bd.workload, x) });
             }
             results = batch;
             idx = { { 0, 1 }, { 0, 1 }, { 0, batch } };

@@ -1,5 +1,5 @@
 """The HEBench-facing plugin (libhebench_seal_backend.so): exports, descriptor set, and the full
-encode -> encrypt -> load -> operate -> store -> decrypt -> decode flow of all 20 benchmarks, validated
+encode -> encrypt -> load -> operate -> store -> decrypt -> decode flow of all 24 benchmarks (the reference's 20 + logistic regression with degree-5 / degree-7 sigmoids), validated
 at value level by the mini harness like the reference's CI does with test_harness
 (R/.github/workflows/cmake.yml:40-49: grep "Failed: 0")."""
 import ctypes
@@ -46,20 +46,25 @@ def test_plugin_exports_api_bridge(built):
 
 
 def test_plugin_descriptor_set(built):
-    """20 descriptors in the reference's order (R/src/engine/seal_engine.cpp:108-151)"""
+    """the reference's 20 descriptors in the reference's order (R/src/engine/seal_engine.cpp:108-151), then the
+    api-bridge's degree-5 / degree-7 logistic-regression workloads (BASELINE.json configs[4]; not in the reference)"""
     out = subprocess.run([HARNESS, "--backend_lib_path", PLUGIN, "--list"], capture_output=True, text=True, check=True).stdout
     lines = [l for l in out.splitlines() if re.match(r"\s*\d+:", l)]
-    assert len(lines) == 20
+    assert len(lines) == 24
     want = (["EltwiseAdd BFV Latency", "EltwiseAdd CKKS Latency", "EltwiseAdd BFV Offline", "EltwiseAdd CKKS Offline",
              "EltwiseMultiply BFV Latency", "EltwiseMultiply CKKS Latency", "EltwiseMultiply BFV Offline", "EltwiseMultiply CKKS Offline",
              "DotProduct BFV Latency", "DotProduct CKKS Latency", "DotProduct BFV Offline", "DotProduct CKKS Offline",
              "MatrixMultiply BFV Latency other=1", "MatrixMultiply CKKS Latency other=1", "MatrixMultiply BFV Latency other=0",
              "MatrixMultiply CKKS Latency other=0", "MatrixMultiply BFV Latency other=2", "MatrixMultiply CKKS Latency other=2",
-             "LogisticRegression_PolyD3 CKKS Latency other=1", "LogisticRegression_PolyD3 CKKS Offline other=1"])
+             "LogisticRegression_PolyD3 CKKS Latency other=1", "LogisticRegression_PolyD3 CKKS Offline other=1",
+             "LogisticRegression_PolyD5 CKKS Latency other=1", "LogisticRegression_PolyD5 CKKS Offline other=1",
+             "LogisticRegression_PolyD7 CKKS Latency other=1", "LogisticRegression_PolyD7 CKKS Offline other=1"])
     for line, w in zip(lines, want):
         assert w in line, (line, w)
     assert "n=1000 PolyModulusDegree=8192 MultiplicativeDepth=2 CoefficientModulusBits=45 ScaleBits=45" in lines[1]
     assert "PolyModulusDegree=16384 MultiplicativeDepth=6 CoefficientModulusBits=45" in lines[19]
+    assert "PolyModulusDegree=32768 MultiplicativeDepth=8 CoefficientModulusBits=45" in lines[21]
+    assert "PolyModulusDegree=32768 MultiplicativeDepth=10 CoefficientModulusBits=45" in lines[23]
 
 
 def test_plugin_fails_loudly_without_gpu(built):
@@ -72,20 +77,20 @@ def test_plugin_fails_loudly_without_gpu(built):
 
 
 def test_workload_logic_on_emulation(emu_lib):
-    """TEST INFRASTRUCTURE: the same backend sources linked against the host-C++ emulation of the kernels, all 20
+    """TEST INFRASTRUCTURE: the same backend sources linked against the host-C++ emulation of the kernels, all 24
     benchmarks at N = 2048, validated against cleartext ground truth"""
     subprocess.check_call(["make", "-s", "-C", BACKEND, "emu"])
     emu_plugin = os.path.join(ROOT, "tests", "emu", "libhebench_seal_backend_emu.so")
     p = subprocess.run([HARNESS, "--backend_lib_path", emu_plugin, "--poly", "2048", "--n", "16", "--dims", "4,3,2", "--batch", "5",
                         "--iterations", "1"], capture_output=True, text=True, timeout=900)
-    assert "[ Info    ] Total: 20" in p.stdout and "[ Info    ] Failed: 0" in p.stdout, p.stdout[-3000:]
+    assert "[ Info    ] Total: 24" in p.stdout and "[ Info    ] Failed: 0" in p.stdout, p.stdout[-3000:]
 
 
 @pytest.mark.gpu
 def test_all_benchmarks_default_parameters_on_gpu(built):
     """the reference CI's check: every benchmark with its default parameters, decoded results validated"""
     p = subprocess.run([HARNESS, "--backend_lib_path", PLUGIN, "--random_seed", "1234"], capture_output=True, text=True, timeout=1500)
-    assert "[ Info    ] Total: 20" in p.stdout and "[ Info    ] Failed: 0" in p.stdout, p.stdout[-4000:]
+    assert "[ Info    ] Total: 24" in p.stdout and "[ Info    ] Failed: 0" in p.stdout, p.stdout[-4000:]
 
 
 @pytest.mark.gpu
@@ -94,7 +99,8 @@ def test_baseline_config_shapes_on_gpu(built):
     C1 BFV eltwise multiply n=100 N=8192; C3 CKKS dot n=100 N=16384; C5 CKKS logreg N=32768"""
     runs = [["--filter", "EltwiseMultiply BFV Offline", "--n", "100", "--samples", "10,10"],
             ["--filter", "DotProduct CKKS Offline", "--n", "100", "--poly", "16384", "--samples", "20,10"],
-            ["--filter", "LogisticRegression_PolyD3 CKKS Offline", "--poly", "32768", "--batch", "64"]]
+            ["--filter", "LogisticRegression_PolyD3 CKKS Offline", "--poly", "32768", "--batch", "64"],
+            ["--filter", "LogisticRegression_PolyD7 CKKS Offline", "--batch", "64"]]
     for extra in runs:
         p = subprocess.run([HARNESS, "--backend_lib_path", PLUGIN] + extra, capture_output=True, text=True, timeout=1500)
         assert "[ Info    ] Failed: 0" in p.stdout and "Total: 1" in p.stdout, p.stdout[-3000:]
