@@ -247,6 +247,7 @@ def run_b200(args):
     a_pin = torch.from_numpy(a_np.view(np.int64).reshape(-1)).pin_memory()
     b_pin = torch.from_numpy(b_np.view(np.int64).reshape(-1)).pin_memory()
     out_pin = torch.empty(BATCH * words_out, dtype=torch.int64).pin_memory()
+    out_pin2 = torch.empty(BATCH * words_out, dtype=torch.int64).pin_memory()   # e2e results alternate between the two
     A, B, R = hb.Batch(ctx), hb.Batch(ctx), hb.Batch(ctx)
     A.resize(BATCH, 2, L, True, scale)
     B.resize(BATCH, 2, L, True, scale)
@@ -274,7 +275,15 @@ def run_b200(args):
         bufs[2].resize(CHUNK, 3, L, True, scale)   # sized for the largest intermediate (the size-3 product)
         e2e.append((cx, st, bufs))
 
-    def e2e_step():
+    # Steps are pipelined one deep, as a streaming service would run them: step i's chunks are enqueued, then the host
+    # waits for step i-1's results (complete in their own pinned buffer) while the copy engines already work on step i,
+    # so the H2D engine never drains between steps.  Every step still moves its inputs host->device and its results
+    # device->host inside the timed region.
+    out_pins = [out_pin, out_pin2]
+    step_done = [[torch.cuda.Event() for _ in range(E2E_STREAMS)] for _ in range(2)]
+
+    def e2e_step(i):
+        dst = out_pins[i % 2]
         for k, first in enumerate(range(0, BATCH, CHUNK)):
             cx, st, (ca, cb, cr) = e2e[k % E2E_STREAMS]
             n = min(CHUNK, BATCH - first)
@@ -282,9 +291,16 @@ def run_b200(args):
             cb.upload_from(b_pin.data_ptr() + first * words_in * 8, 0, n)
             cx.multiply(ca, cb, n=n, out=cr)
             cx.relinearize_rescale(cr, out=cr)
-            cr.download_to(out_pin.data_ptr() + first * words_out * 8, 0, n, wait=False)
+            cr.download_to(dst.data_ptr() + first * words_out * 8, 0, n, wait=False)
+        for s_, (cx, st, _) in enumerate(e2e):
+            step_done[i % 2][s_].record(st)
+        if i > 0:
+            for ev in step_done[(i - 1) % 2]:
+                ev.synchronize()   # the results of step i-1 are on the host
+
+    def e2e_drain():
         for cx, st, _ in e2e:
-            cx.sync()   # results are on the host
+            cx.sync()
 
     def barrier():
         ranks.barrier()
@@ -316,17 +332,18 @@ def run_b200(args):
 
     # ---- end to end through the C ABI with host buffers (pinned): H2D + compute + D2H per step.  Several streams
     # are involved, so the region is bracketed by events on the default stream that every stream joins.
-    for _ in range(2):
-        e2e_step()
+    for i in range(2):
+        e2e_step(i)
+    e2e_drain()
     barrier()
     main = torch.cuda.current_stream()
     ev0.record(main)
     for _, st, _b in e2e:
         st.wait_event(ev0)
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(args.steps):
+        e2e_step(i)
     for _, st, _b in e2e:
-        main.wait_stream(st)
+        main.wait_stream(st)   # the last step's results included
     ev1.record(main)
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
@@ -358,7 +375,8 @@ def run_b200(args):
     chk = ctx.multiply(ctx.batch(a_np[:1], scale=scale), ctx.batch(b_np[:1], scale=scale))
     ctx.relinearize(chk, out=chk)        # the two separate calls: the fused entry must give the same bits
     ctx.rescale_to_next(chk, out=chk)
-    got = out_pin.numpy()[:words_out].view(np.uint64)
+    e2e_drain()
+    got = out_pins[(args.steps - 1) % 2].numpy()[:words_out].view(np.uint64)
     assert np.array_equal(got, chk.download().reshape(-1)), "timed path result differs from a fresh evaluation"
 
     if rank != 0:
@@ -395,7 +413,7 @@ def run_b200(args):
         "config": CONFIG, "clocks": clocks,
         "e2e": {"value": samples / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * words_in * 8 * world,
                 "d2h_bytes_per_step": BATCH * words_out * 8 * world, "ms_per_step": e2e_ms / args.steps,
-                "pipeline": f"{E2E_STREAMS} streams x chunks of {CHUNK} ciphertext pairs", "host_binding": numa},
+                "pipeline": f"{E2E_STREAMS} streams x chunks of {CHUNK} ciphertext pairs, steps pipelined one deep (double-buffered results)", "host_binding": numa},
         "gpu_launches": launches * world,
         "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -493,10 +511,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version there at communicator creation) are sent to stderr; the result line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
