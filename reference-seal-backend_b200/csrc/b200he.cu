@@ -134,6 +134,7 @@ struct b200he_ctx {
     int logn = 0, lognl = 0, c = 0;   // N = 2^logn; CTA-local transform 2^lognl; limb split 2^c ways
     u64 t = 0;
     int M = 0;                        // moduli in the tables: K chain primes (+ BEHZ auxiliary primes)
+    int n_sm = 148;                   // multiprocessors of the device (grid of the persistent kernels)
     std::vector<Mod> mods;
     Tables T{};
     void *d_tables = nullptr;
@@ -353,6 +354,7 @@ template <int LG, int CC> static int set_smem_attrs()
 #ifndef B200HE_EMU
     const int bytes = NttCfg<LG>::SMEM_BYTES;
     CK(cudaFuncSetAttribute(k_ntt_fwd<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (CC == 0) CK(cudaFuncSetAttribute(k_ntt_fwd_p<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttFwdPCfg<LG>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_ntt_inv<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
@@ -390,6 +392,11 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
 #endif
     CK(cudaSetDevice(device));
     b200he_ctx *c = new b200he_ctx;
+#ifndef B200HE_EMU
+    cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
+#else
+    c->n_sm = 3;   // emulation: a few CTAs, several limbs each
+#endif
     c->scheme = scheme;
     c->device = device;
     c->N = N;
@@ -768,6 +775,13 @@ static bool same_scale(double a, double b) { return fabs(a - b) <= 1e-9 * fmax(f
 static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base)
 {
     if (!nlimbs) return 0;
+    static const bool persistent = !(getenv("B200HE_NO_PERSISTENT") && atoi(getenv("B200HE_NO_PERSISTENT")));
+    if (c->c == 0 && persistent && nlimbs > (size_t)c->n_sm) {   // unsplit limbs, more than one wave: persistent CTAs with TMA prefetch
+        NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_NTT_FWD, k_ntt_fwd_p<LG>, (unsigned)c->n_sm, NttCfg<LG>::THREADS, NttFwdPCfg<LG>::SMEM_BYTES, c->T, src, dst,
+                               src_outer, dst_outer, L, mod_base, (int)nlimbs));
+        LAUNCH_CHECK();
+        return 0;
+    }
     KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_FWD, (k_ntt_fwd<LG, CC>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
                                c->T, src, dst, src_outer, dst_outer, L, mod_base));
     LAUNCH_CHECK();

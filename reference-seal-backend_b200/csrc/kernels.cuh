@@ -325,6 +325,65 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd(Tables T, con
     for_pairs_co(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
 }
 
+// Persistent variant for unsplit limbs: one CTA per SM walks the limbs w = blockIdx.x, blockIdx.x + gridDim.x, ...
+// With one 512-thread CTA per SM nothing overlaps a CTA's first global loads; here the next limb's 8 NL bytes arrive by
+// a TMA bulk copy in a second shared-memory buffer while the current limb is transformed, the first pass reads them with
+// conflict-free 128-bit shared loads, and the stores of a limb drain behind the next limb's arithmetic.
+template <int LOGN> struct NttFwdPCfg {
+    static constexpr int SMEM_BYTES = 2 * NttCfg<LOGN>::SMEM_BYTES + 16;   // transform buffer | landing buffer | mbarrier
+};
+template <int LOGN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd_p(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
+                                                                     size_t src_outer, size_t dst_outer, int L, int mod_base, int nlimbs)
+{
+    constexpr int NL = 1 << LOGN;
+    u64 *sm = dyn_smem();
+    u64 *land = sm + NL, *bar = sm + 2 * NL;
+    const int tid = threadIdx.x;
+    auto limb_src = [&](int w) { return src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N; };
+    // round `it` gives CTA b limb it G + (b + it) mod G: consecutive rounds of a CTA land on different moduli, so the
+    // slow (60-bit) and fast (FP64-domain) limbs spread evenly over the SMs whatever G mod L is
+    const int G = gridDim.x, b = blockIdx.x;
+    auto limb_of = [&](int it) { return it * G + (b + it) % G; };
+    if (tid == 0) {
+        tma_bar_init(bar);
+        tma_bar_expect(bar, NL * 8);
+        tma_load_1d(land, limb_src(limb_of(0)), NL * 8, bar);
+    }
+    __syncthreads();   // the barrier is initialised before anyone waits on it
+    u32 phase = 0;
+    for (int it = 0; limb_of(it) < nlimbs; it++, phase ^= 1) {
+        const int w = limb_of(it);
+        const int mid = mod_base + (w % L);
+        const Mod m = T.mods[mid];
+        const ulonglong2 *tw = T.tw + (size_t)mid * T.N;
+        u64 x[16];
+        TwRegs<LOGN, 0> t0;
+        load_tw_early<LOGN, 0, false>(t0, tw, tid, 1);
+        tma_bar_wait(bar, phase);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            const ulonglong2 v = ld2(land + e);
+            x[reg] = v.x;
+            x[reg + 1] = v.y;
+        });
+        if (m.dp) to_dp_all(x);
+        // every thread has read the landing buffer (and finished with the transform buffer of the previous limb): the
+        // next limb's copy may start
+        __syncthreads();
+        if (tid == 0 && limb_of(it + 1) < nlimbs) {
+            tma_bar_expect(bar, NL * 8);
+            tma_load_1d(land, limb_src(limb_of(it + 1)), NL * 8, bar);
+        }
+        ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, 0, 0, t0);
+        u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N;
+        canon_all(x, m);
+        contig_to_co(x, sm, tid);
+        for_pairs_co(tid, [&](int reg, int e) { st2(out + e, x[reg], x[reg + 1]); });
+        // (the warp's slice of the transform buffer is read only by this warp; its next use is the first-pass store of the
+        //  next limb, which sits behind the CTA-wide barrier above)
+    }
+}
+
 // ------------------------------------------------------------------------------------ K2
 enum { INV_PLAIN = 0, INV_ADDHALF = 1 };
 __device__ __forceinline__ u64 inv_finish(u64 v /* [0,2q) */, const Mod &m, int mode)

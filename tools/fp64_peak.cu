@@ -314,6 +314,34 @@ int main()
         printf(" \"bfly_int_shoup_60bit\": {\"ms\": %.4f, \"Gbfly_per_s\": %.1f, \"cycles_per_warp_bfly_per_smsp\": %.2f},\n", ms, bf / ms / 1e6,
                (ms * 1e-3) * (clk * 1e3) * sms * 4 / (bf / 32));
     }
+    // ---- the same butterflies at the occupancy of the NTT kernels: ONE 512-thread CTA per SM (4 warps per scheduler),
+    // forced by a 200 KB dynamic shared-memory request; the rows above run 4 CTAs per SM (16 warps per scheduler)
+    {
+        const int smem = 200 * 1024;
+        cudaFuncSetAttribute(k_bfly_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_bfly_hyb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_bfly_int, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const u64 q45 = 0x1ffffff8c001ull, q60 = 0xffffffffffe8001ull;
+        DpTw dt;
+        HybTw ht;
+        for (int s = 0; s < 4; s++) {
+            const u64 w = (0x123456789abcdefull * (s + 3)) % q45;
+            dt.w[s] = (double)w;
+            dt.wq[s] = (double)((long double)w / (long double)q45);
+            ht.w[s] = (0x123456789abcdefull * (s + 3)) % q60;
+            ht.w2[s] = (u64)(((u128)ht.w[s] << 32) % q60);
+            ht.wq[s] = (double)((long double)ht.w[s] / (long double)q60);
+            ht.w2q[s] = (double)((long double)ht.w2[s] / (long double)q60);
+        }
+        const double qd = (double)q45, qinv = 1.0 / qd;
+        const double bf = (double)grid * 512 * (ITERS / 4) * 32;
+        float ms = time_ms([&] { k_bfly_dp<<<grid, 512, smem>>>(out, dt, qd, qinv, qinv, ITERS / 4, 0); });
+        printf(" \"bfly_dp_45bit_one_cta_per_sm\": {\"ms\": %.4f, \"Gbfly_per_s\": %.1f, \"cycles_per_warp_bfly_per_smsp\": %.2f},\n", ms, bf / ms / 1e6,
+               (ms * 1e-3) * (clk * 1e3) * sms * 4 / (bf / 32));
+        ms = time_ms([&] { k_bfly_int<<<grid, 512, smem>>>(out, ht, q60, ITERS / 4); });
+        printf(" \"bfly_int_shoup_60bit_one_cta_per_sm\": {\"ms\": %.4f, \"Gbfly_per_s\": %.1f, \"cycles_per_warp_bfly_per_smsp\": %.2f},\n", ms, bf / ms / 1e6,
+               (ms * 1e-3) * (clk * 1e3) * sms * 4 / (bf / 32));
+    }
     printf(" \"note\": \"clock_khz is the attribute (max boost)\"}\n");
     return 0;
 }
