@@ -860,6 +860,8 @@ template <int OP> __global__ void __launch_bounds__(256) k_ew(Tables T, EwArgs A
     ulonglong2 vb = ld2(A.b + ib * A.b_stride + boff);
     if (OP == EW_ADD) st2(o, add_mod(va.x, vb.x, m.q), add_mod(va.y, vb.y, m.q));
     else if (OP == EW_SUB) st2(o, sub_mod(va.x, vb.x, m.q), sub_mod(va.y, vb.y, m.q));
+    else if (m.dp)
+        st2(o, dp_canon(dp_mul_dd(dp_from(va.x), dp_from(vb.x), m.dqinv, m.dnq), m), dp_canon(dp_mul_dd(dp_from(va.y), dp_from(vb.y), m.dqinv, m.dnq), m));
     else st2(o, mul_mod(va.x, vb.x, m), mul_mod(va.y, vb.y, m));
 }
 
@@ -876,6 +878,16 @@ __global__ void __launch_bounds__(256) k_tensor(Tables T, EwArgs A)
     const u64 *pa = A.a + ia * A.a_stride + rem, *pb = A.b + ib * A.b_stride + rem;
     ulonglong2 a0 = ld2(pa), a1 = ld2(pa + LN), b0 = ld2(pb), b1 = ld2(pb + LN);
     u64 *o = A.out + i * A.out_stride + rem;
+    if (m.dp) {   // FP64 domain (warp-uniform: a warp's coefficient pairs belong to one limb): 4 exact products per coefficient
+        const double qi = m.dqinv, nq = m.dnq;
+        const double x0 = dp_from(a0.x), x1 = dp_from(a1.x), y0 = dp_from(b0.x), y1 = dp_from(b1.x);
+        const double u0 = dp_from(a0.y), u1 = dp_from(a1.y), v0 = dp_from(b0.y), v1 = dp_from(b1.y);
+        st2(o, dp_canon(dp_mul_dd(x0, y0, qi, nq), m), dp_canon(dp_mul_dd(u0, v0, qi, nq), m));
+        st2(o + LN, dp_canon(__dadd_rn(dp_mul_dd(x0, y1, qi, nq), dp_mul_dd(x1, y0, qi, nq)), m),
+            dp_canon(__dadd_rn(dp_mul_dd(u0, v1, qi, nq), dp_mul_dd(u1, v0, qi, nq)), m));
+        st2(o + 2 * LN, dp_canon(dp_mul_dd(x1, y1, qi, nq), m), dp_canon(dp_mul_dd(u1, v1, qi, nq), m));
+        return;
+    }
     st2(o, mul_mod(a0.x, b0.x, m), mul_mod(a0.y, b0.y, m));
     st2(o + LN, mad_mod(a0.x, b1.x, mul_mod(a1.x, b0.x, m), m), mad_mod(a0.y, b1.y, mul_mod(a1.y, b0.y, m), m));
     st2(o + 2 * LN, mul_mod(a1.x, b1.x, m), mul_mod(a1.y, b1.y, m));

@@ -164,6 +164,14 @@ __device__ __forceinline__ double dp_reduce(double x, double qinv, double nq)
 {
     return __fma_rn(__dadd_rn(__fma_rn(x, qinv, B200HE_DP_MAGIC), -B200HE_DP_MAGIC), nq, x);
 }
+// data x data product a*b mod q + e q for |a|, |b| < 2^46 (no precomputed quotient): |result| <= 0.52 q
+__device__ __forceinline__ double dp_mul_dd(double a, double b, double qinv, double nq)
+{
+    const double h = __dmul_rn(a, b);
+    const double l = __fma_rn(a, b, -h);
+    const double k = __dadd_rn(__fma_rn(h, qinv, B200HE_DP_MAGIC), -B200HE_DP_MAGIC);
+    return __dadd_rn(__fma_rn(k, nq, h), l);
+}
 // lazy value (|x| <= 16 q) -> canonical residue in [0, q) as an integer
 __device__ __forceinline__ u64 dp_canon(double x, const Mod &m)
 {

@@ -136,6 +136,12 @@ def case_extremes(env):
         for l in range(L):
             eq(f[i, 0, l], env.orc.ntt(l, x[i, 0, l]), f"extremes fwd pattern{i} limb{l}")
             eq(g[i, 1, l], env.orc.ntt(l, x[i, 1, l], inverse=True), f"extremes inv pattern{i} limb{l}")
+    if env.scheme == CKKS:   # dyadic products of the extreme patterns, every pattern against every pattern
+        X2 = env.batch(np.ascontiguousarray(x[:, :2]), size=2, L=L)
+        ai, bi = np.repeat(np.arange(4), 4), np.tile(np.arange(4), 4)
+        got = env.ctx.multiply(X2, X2, ai, bi).download()
+        for r in range(16):
+            eq(got[r], env.orc.ckks_multiply(L, x[ai[r], :2].reshape(-1), x[bi[r], :2].reshape(-1)), f"extremes multiply {ai[r]}x{bi[r]}")
     key = np.empty((L, 2, env.K, N), dtype=np.uint64)
     for k in range(env.K):
         key[:, :, k, :] = env.moduli[k] - np.uint64(1)
