@@ -45,14 +45,34 @@ __device__ __forceinline__ u64 *dyn_smem()
 }
 
 // Input transforms fused into the first-pass load: pair(v, idx) maps the coefficient pair at limb index idx, idx+1.
-struct PreNone { __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return v; } };
+// (a functor whose pair() already returns FP64-domain values declares gives_dp: load_fwd_split then skips its own conversion)
+struct PreNone {
+    static constexpr bool gives_dp = false;
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return v; }
+};
+// Lift of a residue of a wide modulus (up to 61 bits: more than a double's mantissa) into an FP64-domain modulus,
+// without an integer multiply: v = vh 2^30 + vl, lifted value = (2^30 vh mod q) + vl with the product in the FP64 domain
+// (|result| <= 0.75 q + 2^30).  Residues of moduli of at most 48 bits need no lift at all: the transform accepts any
+// integer of magnitude below 2^48 as a lazy value (its outputs then stay below 2^48 + 14 q < 2^50), so they use PreNone.
+struct PreLiftDp {
+    static constexpr bool gives_dp = true;
+    double wq, nq;   // RN(2^30 / q), -q
+    __device__ __forceinline__ u64 one(u64 v) const
+    {
+        const double hi = dp_from(v >> 30), lo = dp_from(v & 0x3fffffffull);
+        return as_u(__dadd_rn(dp_mul(hi, 1073741824.0, wq, nq), lo));
+    }
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(one(v.x), one(v.y)); }
+};
 // (the functors carry q and floor(2^64/q) only: a by-value copy of the whole Mod lands in local memory)
 __device__ __forceinline__ u64 reduce64_qr(u64 x, u64 q, u64 r64) { return csub(x - mulhi64(x, r64) * q, q); }
 struct PreReduce {   // v mod q (lift of a digit into another modulus, SEAL modulo_poly_coeffs)
+    static constexpr bool gives_dp = false;
     u64 q, r64;
     __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64_qr(v.x, q, r64), reduce64_qr(v.y, q, r64)); }
 };
 struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_last/2 mod q))
+    static constexpr bool gives_dp = false;
     u64 q, r64, fix;
     __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64_qr(v.x, q, r64) + fix, reduce64_qr(v.y, q, r64) + fix); }
 };
@@ -60,6 +80,7 @@ struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_l
 // NTT(u1) * s * r (key switch, s = q_sp^{-1}) and NTT(u2) * r (rescale, r = q_last^{-1}), are one transform of
 // (u1 * s + u2) * r because the transform is linear over Z_q.  Result in [0, 2q).
 struct PreTwo {
+    static constexpr bool gives_dp = false;
     u64 q, r64;
     u64 fix1, fix2;
     ulonglong2 s, r;
@@ -289,7 +310,9 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
         x[reg] = v.x;
         x[reg + 1] = v.y;
     });
-    if (m.dp) to_dp_all(x);
+    if constexpr (!Pre::gives_dp) {
+        if (m.dp) to_dp_all(x);
+    }
     if (c > 0) {
         if (REUSE) __syncthreads();
         cross_fwd<LOGN>(x, sm, c, r, tid, tw, m);
@@ -543,7 +566,12 @@ __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs
             const u64 *tp = A.tcoef + (size_t)b * A.tcoef_stride + (size_t)J * N;
             TwRegs<LOGN, 0> t0;
             load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
-            if (T.mods[J].q > m.q)
+            if constexpr (DP) {   // FP64 domain: digits of moduli up to 48 bits are lazy values as they are (2^48 + 14 q < 2^50)
+                if (T.mods[J].bits > 48)
+                    load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreLiftDp{ 1073741824.0 * m.dqinv, m.dnq }, sm);
+                else
+                    load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
+            } else if (T.mods[J].q > m.q)
                 load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce{ m.q, m.r64 }, sm);
             else
                 load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
