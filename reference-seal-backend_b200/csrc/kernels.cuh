@@ -66,20 +66,26 @@ struct PreLiftDp {
 };
 // (the functors carry q and floor(2^64/q) only: a by-value copy of the whole Mod lands in local memory)
 __device__ __forceinline__ u64 reduce64_qr(u64 x, u64 q, u64 r64) { return csub(x - mulhi64(x, r64) * q, q); }
-struct PreReduce {   // v mod q (lift of a digit into another modulus, SEAL modulo_poly_coeffs)
+// Lifting a residue of modulus q_x (a value below q_x) into modulus q needs a Barrett reduction only when q_x >= 2q;
+// for q_x < 2q -- two 60-bit primes, two 45-bit primes -- one conditional subtraction does it.  WIDE is a template
+// parameter: callers branch once on lift_wide() and instantiate both (a CTA-uniform flag inside the functor cost more in
+// code shape than the multiplies it saved).
+__device__ __forceinline__ bool lift_wide(u64 qx, u64 q) { return qx >= 2 * q; }
+template <bool WIDE> __device__ __forceinline__ u64 lift(u64 v, u64 q, u64 r64) { return WIDE ? reduce64_qr(v, q, r64) : csub(v, q); }
+template <bool WIDE> struct PreReduce {   // v mod q (lift of a digit into another modulus, SEAL modulo_poly_coeffs)
     static constexpr bool gives_dp = false;
     u64 q, r64;
-    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64_qr(v.x, q, r64), reduce64_qr(v.y, q, r64)); }
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(lift<WIDE>(v.x, q, r64), lift<WIDE>(v.y, q, r64)); }
 };
-struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_last/2 mod q))
+template <bool WIDE> struct PreReduceFix {   // (v mod q) + fix   (mod-down / rescale: fix = q - (q_last/2 mod q))
     static constexpr bool gives_dp = false;
     u64 q, r64, fix;
-    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(reduce64_qr(v.x, q, r64) + fix, reduce64_qr(v.y, q, r64) + fix); }
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const { return make_ulonglong2(lift<WIDE>(v.x, q, r64) + fix, lift<WIDE>(v.y, q, r64) + fix); }
 };
 // Fused relinearize + rescale (k_moddown with two rounded limbs): the two mod-down corrections of output limb j,
 // NTT(u1) * s * r (key switch, s = q_sp^{-1}) and NTT(u2) * r (rescale, r = q_last^{-1}), are one transform of
 // (u1 * s + u2) * r because the transform is linear over Z_q.  Result in [0, 2q).
-struct PreTwo {
+template <bool WIDE> struct PreTwo {
     static constexpr bool gives_dp = false;
     u64 q, r64;
     u64 fix1, fix2;
@@ -87,8 +93,8 @@ struct PreTwo {
     const u64 *rp2;
     __device__ __forceinline__ u64 one(u64 v1, u64 v2) const
     {
-        const u64 a = shoup_lazy(reduce64_qr(v1, q, r64) + fix1, s.x, s.y, q);
-        return shoup_lazy(a + reduce64_qr(v2, q, r64) + fix2, r.x, r.y, q);
+        const u64 a = shoup_lazy(lift<WIDE>(v1, q, r64) + fix1, s.x, s.y, q);
+        return shoup_lazy(a + lift<WIDE>(v2, q, r64) + fix2, r.x, r.y, q);
     }
     __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t idx) const
     {
@@ -571,8 +577,10 @@ __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs
                     load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreLiftDp{ 1073741824.0 * m.dqinv, m.dnq }, sm);
                 else
                     load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
-            } else if (T.mods[J].q > m.q)
-                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce{ m.q, m.r64 }, sm);
+            } else if (lift_wide(T.mods[J].q, m.q))
+                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce<true>{ m.q, m.r64 }, sm);
+            else if (T.mods[J].q > m.q)
+                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce<false>{ m.q, m.r64 }, sm);
             else
                 load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
             ntt_fwd_regs_split<LOGN, true>(x, sm, tw, m, tid, c, r, t0, prefetch_key0);
@@ -789,8 +797,12 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
     if (A.rp2) {
         const ulonglong2 ri = T.qinv[(size_t)A.x2 * T.M + j];
         const u64 fix2 = m.q - T.halfmod[(size_t)A.x2 * T.M + j];
-        load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
-                             PreTwo{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
+        if (lift_wide(T.mods[A.x].q, m.q) || lift_wide(T.mods[A.x2].q, m.q))
+            load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
+                                 PreTwo<true>{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
+        else
+            load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
+                                 PreTwo<false>{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
         ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
         canon_all(x, m);
         contig_to_co(x, sm, tid);
@@ -803,7 +815,10 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         });
         return;
     }
-    load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix{ m.q, m.r64, fix }, sm);
+    if (lift_wide(T.mods[A.x].q, m.q))
+        load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix<true>{ m.q, m.r64, fix }, sm);
+    else
+        load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix<false>{ m.q, m.r64, fix }, sm);
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     canon_all(x, m);
     contig_to_co(x, sm, tid);
