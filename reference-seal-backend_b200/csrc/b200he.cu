@@ -358,11 +358,14 @@ template <int LG, int CC> static int set_smem_attrs()
     CK(cudaFuncSetAttribute(k_ntt_inv<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_moddown_dp<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_moddown_mix<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
 #endif
     return 0;
 }
 
 static int init_behz(b200he_ctx *c, std::vector<u64> &moduli, std::vector<u64> &psi);
+struct b200he_ctx;
 static int stage_init(b200he_ctx *c, size_t ct_bytes);
 static int upload_behz(b200he_ctx *c);
 
@@ -772,6 +775,25 @@ static bool same_scale(double a, double b) { return fabs(a - b) <= 1e-9 * fmax(f
 
 // ------------------------------------------------------------------------------------ transforms
 // forward NTT of nlimbs limbs (grouped L per outer stride).  In place only when the limb is unsplit.
+// k_moddown over D.nJ output limbs of `polys` polynomials: the kernel that holds only the integer instance, only the
+// FP64 instance, or both, by the kinds of moduli among those limbs
+static void launch_moddown(b200he_ctx *c, ModDownArgs D, size_t polys)
+{
+    unsigned dpmask = 0;
+    for (int j = 0; j < D.nJ; j++)
+        if (c->mods[j].dp) dpmask |= 1u << j;
+    const unsigned all = D.nJ >= 32 ? ~0u : ((1u << D.nJ) - 1);
+    D.jmask = all;
+    D.nJsub = D.nJ;
+    const unsigned grid = (unsigned)((polys * D.nJ) << c->c);
+    if (dpmask == 0) {
+        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, c->T, D));
+    } else if (dpmask == all) {
+        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown_dp<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, c->T, D));
+    } else {
+        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown_mix<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, c->T, D));
+    }
+}
 static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base)
 {
     if (!nlimbs) return 0;
@@ -1046,11 +1068,9 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
             rc = ntt_inv(c, acc + (size_t)(L - 1) * N, rp2, nb * 2, (size_t)(L + 1) * N, N, 1, L - 1, INV_ADDHALF, &F);
             if (rc) break;
             D.rp2 = rp2; D.x2 = L - 1; D.nJ = L - 1; D.out_poly_stride = (size_t)(L - 1) * N;
-            KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * 2 * (L - 1)) << c->c), NttCfg<LG>::THREADS,
-                                   ModDownCfg<LG>::SMEM_BYTES, c->T, D));
+            launch_moddown(c, D, nb * 2);
         } else if (ckks) {
-            KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * 2 * L) << c->c), NttCfg<LG>::THREADS,
-                                   ModDownCfg<LG>::SMEM_BYTES, c->T, D));
+            launch_moddown(c, D, nb * 2);
         } else {
             // BFV: accumulators back to coefficient form (in place, unsplit per-limb strides), then elementwise mod-down
             rc = ntt_inv(c, acc, acc, nb * 2 * L, (size_t)(L + 1) * N, (size_t)(L + 1) * N, L, 0, INV_PLAIN);
@@ -1359,8 +1379,7 @@ extern "C" int b200he_rescale_to_next(b200he_ctx *c, const b200he_batch *in, b20
             rc = ntt_inv(c, src + (size_t)(L - 1) * N, rp, nb * P, (size_t)L * N, N, 1, L - 1, INV_ADDHALF);
             if (rc) break;
             D.rp = rp;
-            KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), (unsigned)((nb * P * (L - 1)) << c->c), NttCfg<LG>::THREADS,
-                                   ModDownCfg<LG>::SMEM_BYTES, c->T, D));
+            launch_moddown(c, D, nb * P);
         } else {
             // coefficient form: rp = last + q_last/2 mod q_last, elementwise
             D.rp = nullptr; D.rp_raw = src + (size_t)(L - 1) * N; D.rp_raw_stride = (size_t)L * N;

@@ -66,6 +66,36 @@ struct PreLiftDp {
 };
 // (the functors carry q and floor(2^64/q) only: a by-value copy of the whole Mod lands in local memory)
 __device__ __forceinline__ u64 reduce64_qr(u64 x, u64 q, u64 r64) { return csub(x - mulhi64(x, r64) * q, q); }
+// FP64-domain versions of the mod-down input transforms (k_moddown, FP64 instance).  W* = the source modulus is wider
+// than 48 bits (split lift); narrower residues are lazy values as they are.
+template <bool W> __device__ __forceinline__ double lift_dp(u64 v, double wq30, double nq)
+{
+    if (!W) return dp_from(v);
+    return __dadd_rn(dp_mul(dp_from(v >> 30), 1073741824.0, wq30, nq), dp_from(v & 0x3fffffffull));
+}
+template <bool W> struct PreReduceFixDp {   // lift(v) + fix
+    static constexpr bool gives_dp = true;
+    double wq30, nq, fix;
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t) const
+    {
+        return make_ulonglong2(as_u(__dadd_rn(lift_dp<W>(v.x, wq30, nq), fix)), as_u(__dadd_rn(lift_dp<W>(v.y, wq30, nq), fix)));
+    }
+};
+template <bool W1, bool W2> struct PreTwoDp {   // ((lift(u1) + fix1) s + lift(u2) + fix2) r, see PreTwo
+    static constexpr bool gives_dp = true;
+    double wq30, nq, fix1, fix2, s, sq, r, rq;
+    const u64 *rp2;
+    __device__ __forceinline__ u64 one(u64 v1, u64 v2) const
+    {
+        const double a = dp_mul(__dadd_rn(lift_dp<W1>(v1, wq30, nq), fix1), s, sq, nq);
+        return as_u(dp_mul(__dadd_rn(__dadd_rn(a, lift_dp<W2>(v2, wq30, nq)), fix2), r, rq, nq));
+    }
+    __device__ __forceinline__ ulonglong2 pair(ulonglong2 v, size_t idx) const
+    {
+        const ulonglong2 w = ldg2(rp2 + idx);
+        return make_ulonglong2(one(v.x, w.x), one(v.y, w.y));
+    }
+};
 // Lifting a residue of modulus q_x (a value below q_x) into modulus q needs a Barrett reduction only when q_x >= 2q;
 // for q_x < 2q -- two 60-bit primes, two 45-bit primes -- one conditional subtraction does it.  WIDE is a template
 // parameter: callers branch once on lift_wide() and instantiate both (a CTA-uniform flag inside the functor cost more in
@@ -737,6 +767,19 @@ __global__ void __launch_bounds__(256) k_shoup_quotients(Tables T, const u64 *__
 // rp = rounded last limb in coefficient form ((iNTT(last) + q_x/2) mod q_x), x = modulus id of the dropped prime.
 // Key switch:  base = acc (stride over L+1 limbs), addend = input ct component (or none), x = K-1.
 // Rescale:     base = input ct, addend = none, x = L-1.       grid = B * P * nJ << c.
+__device__ __forceinline__ int nth_set_bit(unsigned mask, int n)   // index of the n-th (0-based) set bit
+{
+#if defined(__CUDA_ARCH__)
+    return (int)__fns(mask, 0, n + 1);
+#else
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) {
+            if (n == 0) return i;
+            n--;
+        }
+    return 0;
+#endif
+}
 struct ModDownArgs {
     const u64 *rp;         // [B][P][N]  (k_moddown_coeff: may be nullptr, then rp_raw is used)
     const u64 *rp_raw;     // un-rounded last limb, coefficient form: rp_raw + (b*P + p)*rp_raw_stride
@@ -748,6 +791,10 @@ struct ModDownArgs {
     u64 *out;              // out + b*out_ct_stride + p*out_poly_stride + j*N
     size_t out_ct_stride, out_poly_stride;
     int P, nJ, x;          // x = modulus id of the dropped prime
+    // limbs handled by this launch: bit j of jmask, nJsub = popcount(jmask) (the host launches the integer kernel for
+    // the limbs of wide moduli and the FP64 kernel for the others; jmask = 2^nJ - 1 when there is only one kind)
+    unsigned jmask;
+    int nJsub;
     // fused relinearize + rescale: rp2 = rounded last data limb (coefficient form, [B][P][N]) of the key-switched
     // ciphertext, x2 = its modulus id.  out = (base * s + addend) * r - NTT((u1 * s + u2) * r), s = q_x^{-1}, r = q_x2^{-1}
     const u64 *rp2;
@@ -759,8 +806,11 @@ struct ModDownArgs {
 template <int LOGN> struct ModDownCfg {
     static constexpr int SMEM_BYTES = 3 * NttCfg<LOGN>::SMEM_BYTES + 16;
 };
-template <int LOGN, int C>
-__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, ModDownArgs A)
+// DP = Mod::dp of the output limb's modulus, a compile-time constant (one branch at the top of the kernel, two complete
+// instances, as in k_ks_inner).  In the FP64 instance the lifted input, the transform, and the epilogue's two constant
+// multiplies stay in the FP64 domain; the result leaves it once, in the final store.
+template <int LOGN, int C, bool DP>
+__device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs &A)
 {
     constexpr int c = C;
     constexpr int NL = 1 << LOGN;
@@ -769,10 +819,11 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
     const int tid = threadIdx.x;
     const int r = blockIdx.x & ((1 << c) - 1);
     int unit = blockIdx.x >> c;
-    const int j = unit % A.nJ;
-    unit /= A.nJ;
+    const int j = nth_set_bit(A.jmask, unit % A.nJsub);
+    unit /= A.nJsub;
     const int p = unit % A.P, b = unit / A.P;
-    const Mod m = T.mods[j];
+    Mod m = T.mods[j];
+    m.dp = DP;
     const ulonglong2 *tw = T.tw + (size_t)j * T.N;
     const size_t N = T.N, off = (size_t)r * NL;
     const u64 fix = m.q - T.halfmod[(size_t)A.x * T.M + j];
@@ -793,6 +844,47 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         tma_bar_expect(bar, (ap ? 2u : 1u) * NL * 8);
         tma_load_1d(stage_b, bp, NL * 8, bar);
         if (ap) tma_load_1d(stage_a, ap, NL * 8, bar);
+    }
+    if constexpr (DP) {
+        const double wq30 = 1073741824.0 * m.dqinv, nq = m.dnq;
+        const double sd = dp_from(qi.x), sq = __dmul_rn(sd, m.dqinv);
+        const u64 *rp = A.rp + ((size_t)b * A.P + p) * N;
+        const bool w1 = T.mods[A.x].bits > 48;
+        if (A.rp2) {
+            const double rd = dp_from(T.qinv[(size_t)A.x2 * T.M + j].x), rq = __dmul_rn(rd, m.dqinv);
+            const double fix2 = dp_from(m.q - T.halfmod[(size_t)A.x2 * T.M + j]);
+            const u64 *rp2 = A.rp2 + ((size_t)b * A.P + p) * N;
+            if (w1 && T.mods[A.x2].bits <= 48)   // the usual case: special prime wide, last data prime narrow
+                load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreTwoDp<true, false>{ wq30, nq, dp_from(fix), fix2, sd, sq, rd, rq, rp2 }, sm);
+            else
+                load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreTwoDp<true, true>{ wq30, nq, dp_from(fix), fix2, sd, sq, rd, rq, rp2 }, sm);
+            ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
+            contig_to_co(x, sm, tid);   // FP64-domain values, |x| < 14 q
+            tma_bar_wait(bar, 0);
+            for_pairs_co(tid, [&](int reg, int e) {
+                const ulonglong2 bv = ld2(stage_b + e), av = ld2(stage_a + e);
+                const double g0 = __dadd_rn(dp_mul(dp_from(bv.x), sd, sq, nq), dp_from(av.x)), g1 = __dadd_rn(dp_mul(dp_from(bv.y), sd, sq, nq), dp_from(av.y));
+                const double h0 = dp_mul(g0, rd, rq, nq), h1 = dp_mul(g1, rd, rq, nq);
+                st2(op + e, dp_canon(__dadd_rn(h0, -as_d(x[reg])), m), dp_canon(__dadd_rn(h1, -as_d(x[reg + 1])), m));
+            });
+            return;
+        }
+        if (w1) load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreReduceFixDp<true>{ wq30, nq, dp_from(fix) }, sm);
+        else load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreReduceFixDp<false>{ wq30, nq, dp_from(fix) }, sm);
+        ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
+        contig_to_co(x, sm, tid);
+        tma_bar_wait(bar, 0);
+        for_pairs_co(tid, [&](int reg, int e) {
+            const ulonglong2 bv = ld2(stage_b + e);
+            double v0 = dp_mul(__dadd_rn(dp_from(bv.x), -as_d(x[reg])), sd, sq, nq), v1 = dp_mul(__dadd_rn(dp_from(bv.y), -as_d(x[reg + 1])), sd, sq, nq);
+            if (ap) {
+                const ulonglong2 av = ld2(stage_a + e);
+                v0 = __dadd_rn(v0, dp_from(av.x));
+                v1 = __dadd_rn(v1, dp_from(av.y));
+            }
+            st2(op + e, dp_canon(v0, m), dp_canon(v1, m));
+        });
+        return;
     }
     if (A.rp2) {
         const ulonglong2 ri = T.qinv[(size_t)A.x2 * T.M + j];
@@ -835,6 +927,28 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, Mod
         }
         st2(op + e, v0, v1);
     });
+}
+
+// One kernel per instance, and a third with both for launches that mix limbs of the two kinds: inlined into one kernel,
+// the FP64 instance costs the integer instance registers (spills 24 -> 92 bytes, +12 % on the all-integer mod-down of
+// the C2 step), so launches of a single kind use a kernel that holds only their instance.
+template <int LOGN, int C>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown(Tables T, ModDownArgs A)
+{
+    moddown_body<LOGN, C, false>(T, A);
+}
+template <int LOGN, int C>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown_dp(Tables T, ModDownArgs A)
+{
+    moddown_body<LOGN, C, true>(T, A);
+}
+// limbs of both kinds in one launch (splitting such a launch in two costs more in tails and launch gaps than the
+// shared register allocation costs the integer instance)
+template <int LOGN, int C>
+__global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_moddown_mix(Tables T, ModDownArgs A)
+{
+    if (T.mods[nth_set_bit(A.jmask, ((int)blockIdx.x >> C) % A.nJsub)].dp) moddown_body<LOGN, C, true>(T, A);
+    else moddown_body<LOGN, C, false>(T, A);
 }
 
 // Coefficient-form variant (BFV key switch / BFV mod-switch): no transform, one thread per coefficient pair.
