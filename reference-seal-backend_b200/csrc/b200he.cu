@@ -355,7 +355,9 @@ template <int LG, int CC> static int set_smem_attrs()
     const int bytes = NttCfg<LG>::SMEM_BYTES;
     CK(cudaFuncSetAttribute(k_ntt_fwd<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     if (CC == 0) CK(cudaFuncSetAttribute(k_ntt_fwd_p<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttFwdPCfg<LG>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_ntt_inv<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute((k_ntt_inv<LG, CC, KIND_BOTH>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute((k_ntt_inv<LG, CC, KIND_INT>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute((k_ntt_inv<LG, CC, KIND_DP>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_moddown_dp<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
@@ -815,8 +817,19 @@ static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_
     if (!nlimbs) return 0;
     InvFuse F{};
     if (fuse) F = *fuse;
-    KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                               c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
+    // kinds of moduli among the launch's limbs (modulus ids mod_base .. mod_base + L - 1)
+    int n_dp = 0;
+    for (int l = 0; l < L; l++) n_dp += c->mods[mod_base + l].dp ? 1 : 0;
+    if (n_dp == 0) {
+        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC, KIND_INT>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
+                                   c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
+    } else if (n_dp == L) {
+        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC, KIND_DP>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
+                                   c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
+    } else {
+        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC, KIND_BOTH>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
+                                   c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
+    }
     LAUNCH_CHECK();
     return 0;
 }

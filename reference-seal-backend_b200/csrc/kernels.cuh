@@ -469,7 +469,18 @@ __device__ __forceinline__ u64 inv_post(u64 v /* finished, canonical */, u64 sub
     return sub_mod(v, shoup(reduce64(subv, m) + fix, s.x, s.y, m.q), m.q);
 }
 // dst = iNTT(src), finished (c > 0: the cluster's CTAs exchange the cross-chunk stages through DSMEM).
-template <int LOGN, int C>
+// KIND: 0 = the launch holds limbs of both kinds (Mod::dp decides per CTA); 1 = integer-pipe moduli only; 2 = FP64-domain
+// moduli only.  With the kind known at compile time the other instance is not in the kernel, and its register demands
+// with it (see k_moddown).
+enum { KIND_BOTH = 0, KIND_INT = 1, KIND_DP = 2 };
+template <int KIND> __device__ __forceinline__ Mod load_mod(const Tables &T, int mid)
+{
+    Mod m = T.mods[mid];
+    if (KIND == KIND_INT) m.dp = 0;
+    if (KIND == KIND_DP) m.dp = 1;
+    return m;
+}
+template <int LOGN, int C, int KIND>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
                                                                    size_t src_outer, size_t dst_outer, int L, int mod_base, int mode, InvFuse F)
 {
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     const int tid = threadIdx.x;
     const int w = blockIdx.x >> c, r = blockIdx.x & ((1 << c) - 1);
     const int mid = mod_base + (w % L);
-    const Mod m = T.mods[mid];
+    const Mod m = load_mod<KIND>(T, mid);
     const ulonglong2 *itw = T.itw + (size_t)mid * T.N;
     const u64 *in = src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     u64 x[16];
