@@ -498,6 +498,34 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     load_tw_early<LOGN, Sched<LOGN>::NP - 1, true>(tl, itw, tid, (1 << c) + r);
     ulonglong2 fs = make_ulonglong2(0, 0);
     u64 ffix = 0;
+    if constexpr (C == 0 && KIND != KIND_INT) {
+        if (F.add && m.dp) {
+            // FP64-domain modulus: the fused pre- and post-processing (see InvFuse) stay in the domain -- scaling of the
+            // accumulator, the split lift of the rounded special-prime limb, its scaling and the subtraction -- and
+            // the result leaves it once, in the final store
+            constexpr int NPL = Sched<LOGN>::NP - 1;
+            const double nq = m.dnq, sd = dp_from(T.qinv[(size_t)F.x * T.M + mid].x), sq = __dmul_rn(sd, m.dqinv);
+            const double fixd = dp_from(m.q - T.halfmod[(size_t)F.x * T.M + mid]), wq30 = 1073741824.0 * m.dqinv;
+            const double half = mode == INV_ADDHALF ? dp_from(m.q >> 1) : 0.0;
+            const u64 *ad = F.add + (size_t)(w / F.P) * F.add_ct_stride + (size_t)(w % F.P) * F.add_poly_stride;
+            for_pairs_co(tid, [&](int reg, int e) {
+                const ulonglong2 v = ldg2(in + e), a = ldg2(ad + e);
+                x[reg] = as_u(__dadd_rn(dp_mul(dp_from(v.x), sd, sq, nq), dp_from(a.x)));
+                x[reg + 1] = as_u(__dadd_rn(dp_mul(dp_from(v.y), sd, sq, nq), dp_from(a.y)));
+            });
+            co_to_contig(x, sm, tid);
+            ntt_inv_regs_split<LOGN, true, false, NPL, true, true>(x, sm, itw, m, tid, 0, 0, tl);
+            u64 *outp = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N;
+            const u64 *sb = F.sub + (size_t)w * T.N;
+            for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+                const ulonglong2 u = ldg2(sb + e);
+                const double t0 = dp_mul(__dadd_rn(lift_dp<true>(u.x, wq30, nq), fixd), sd, sq, nq);
+                const double t1 = dp_mul(__dadd_rn(lift_dp<true>(u.y, wq30, nq), fixd), sd, sq, nq);
+                st2(outp + e, dp_canon(__dadd_rn(__dadd_rn(as_d(x[reg]), -t0), half), m), dp_canon(__dadd_rn(__dadd_rn(as_d(x[reg + 1]), -t1), half), m));
+            });
+            return;
+        }
+    }
     if (F.add) {
         fs = T.qinv[(size_t)F.x * T.M + mid];
         ffix = m.q - T.halfmod[(size_t)F.x * T.M + mid];

@@ -404,17 +404,19 @@ __device__ __forceinline__ void ntt_fwd_regs_split(u64 (&x)[16], u64 *sm, const 
 // t = twiddles of the last pass (load_tw_early<LOGN,NP-1,true> on the inverse table).
 // Out: x in pass-0 layout; FINAL (unsplit limb): multiplied by N^{-1}, in [0,2q); otherwise lazy (Mod::dp moduli:
 // FP64-domain values, to be passed through reduce_all and cross_inv).
-template <int LOGN, bool FINAL, bool REUSE = false, int P = Sched<LOGN>::NP - 1>
+// IN_DP / OUT_DP (Mod::dp moduli only): the caller hands over / takes back FP64-domain values (in: magnitude <= 1.75 q,
+// out: <= 0.75 q) instead of canonical integers, because its own pre- / post-processing runs in the domain too.
+template <int LOGN, bool FINAL, bool REUSE = false, int P = Sched<LOGN>::NP - 1, bool IN_DP = false, bool OUT_DP = false>
 __device__ __forceinline__ void ntt_inv_regs_split(u64 (&x)[16], u64 *sm, const ulonglong2 *__restrict__ itw, const Mod &m, int tid, int c, int r,
                                                    TwRegs<LOGN, P> &t)
 {
     ulonglong2 wfold = make_ulonglong2(0, 0);
     if constexpr (FINAL && P == 0) wfold = ld_tw(itw);
-    if constexpr (P == Sched<LOGN>::NP - 1) {
+    if constexpr (P == Sched<LOGN>::NP - 1 && !IN_DP) {
         if (m.dp) to_dp_all(x);
     }
     bfly_inv<LOGN, P, FINAL>(x, t, m, wfold, itw, tid, (1 << c) + r);
-    if constexpr (FINAL && P == 0) {
+    if constexpr (FINAL && P == 0 && !OUT_DP) {
         if (m.dp) canon_all(x, m);   // finished values leave the FP64 domain as canonical integers
     }
     if constexpr (P > 0) {
@@ -424,7 +426,7 @@ __device__ __forceinline__ void ntt_inv_regs_split(u64 (&x)[16], u64 *sm, const 
         smem_xfer<LOGN, P, true>(x, sm, tid);
         xchg_sync<LOGN, P - 1>(tid);
         smem_xfer<LOGN, P - 1, false>(x, sm, tid);
-        ntt_inv_regs_split<LOGN, FINAL, REUSE, P - 1>(x, sm, itw, m, tid, c, r, tn);
+        ntt_inv_regs_split<LOGN, FINAL, REUSE, P - 1, IN_DP, OUT_DP>(x, sm, itw, m, tid, c, r, tn);
     }
 }
 
