@@ -457,6 +457,15 @@ def oracle_setup():
     return np, host, orc
 
 
+def host_threads(orc):
+    """all the host threads the CPU arm can use: the cores this process may run on -- not omp_get_max_threads(), which
+    torchrun pins to 1 through OMP_NUM_THREADS for every rank it launches"""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(orc.o.orc_max_threads(), 1)
+
+
 def cpu_sample(np, host, orc, n, threads):
     a = synth_inputs(host.moduli, n, host.Ltop, N_POLY, SEED).reshape(-1)
     b = synth_inputs(host.moduli, n, host.Ltop, N_POLY, SEED + 1).reshape(-1)
@@ -468,7 +477,7 @@ def cpu_sample(np, host, orc, n, threads):
 
 def cpu_baseline(budget_s=12.0):
     np, host, orc = oracle_setup()
-    threads = orc.o.orc_max_threads()
+    threads = host_threads(orc)
     probe = 4 * threads
     dt = cpu_sample(np, host, orc, probe, threads)
     n = int(max(probe, min(BATCH, probe * budget_s / max(dt, 1e-6))))
@@ -482,7 +491,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     np, host, orc = oracle_setup()
-    threads = orc.o.orc_max_threads()
+    threads = host_threads(orc)
     probe = 4 * threads
     dt = cpu_sample(np, host, orc, probe, threads)
     total_steps = max(args.warmup, 0) + args.steps
