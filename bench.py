@@ -67,8 +67,9 @@ DP_MAX_BITS = 46   # csrc/modarith.cuh B200HE_DP_MAX_BITS: moduli at or below ru
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (NVML; nvidia-smi as a fallback)"""
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, period=0.002):
         self.gpu, self.sm, self.mx, self.reasons, self.stop = gpu, [], None, set(), threading.Event()
+        self.period = period
         self.t = threading.Thread(target=self.run, daemon=True)
         self.n = 0
 
@@ -90,7 +91,7 @@ class ClockSampler:
                     if r & b:
                         self.reasons.add(k)
                 self.n += 1
-                if self.stop.wait(0.002):
+                if self.stop.wait(self.period):
                     break
         except Exception:
             q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -337,10 +338,14 @@ def run_b200(args):
     e2e_drain()
     barrier()
     main = torch.cuda.current_stream()
-    ev0.record(main)
-    for _, st, _b in e2e:
-        st.wait_event(ev0)
-    with ClockSampler(local) as clk2:   # the end-to-end region is timed too: its samples join the device-timed region's
+    # the end-to-end region is timed too: its samples join the device-timed region's (a slower poll: the enqueue loop of
+    # this region is Python and shares the interpreter with the sampling thread).  The sampler starts -- and sleeps its
+    # start-up 10 ms -- before the region opens.
+    with ClockSampler(local, period=0.02) as clk2:
+        barrier()
+        ev0.record(main)
+        for _, st, _b in e2e:
+            st.wait_event(ev0)
         for i in range(args.steps):
             e2e_step(i)
         for _, st, _b in e2e:
