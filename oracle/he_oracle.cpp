@@ -46,11 +46,83 @@ static inline u64 shoup_mul_lazy(u64 y, u64 w, u64 ws, u64 q)
     u64 hi = (u64)(((u128)y * ws) >> 64);
     return y * w - hi * q;
 }
+// Barrett reduction with the two-word ratio floor(2^128 / q) (the form SEAL's Modulus::const_ratio() holds): the hot
+// loops below use it; the plain `%` forms above remain for set-up code and as the checker of this one
+// (orc_selftest_fastmod, tests/test_oracle.py).  Valid for q < 2^62.
+struct FastMod {
+    u64 q = 0, r0 = 0, r1 = 0;   // floor(2^128 / q) = r1 * 2^64 + r0
+    void init(u64 q_)
+    {
+        q = q_;
+        // 2^128 / q by long division of (2^128 - 1) / q: the quotients agree because q does not divide 2^128
+        const u128 all = ~(u128)0;
+        const u128 quo = all / q;
+        r0 = (u64)quo;
+        r1 = (u64)(quo >> 64);
+    }
+    // (hi:lo) mod q for any 128-bit input
+    inline u64 red128(u64 hi, u64 lo) const
+    {
+        u64 carry = (u64)(((u128)lo * r0) >> 64);
+        const u128 t2 = (u128)lo * r1;
+        const u64 tmp1 = (u64)t2 + carry;
+        const u64 tmp3 = (u64)(t2 >> 64) + (tmp1 < carry);
+        const u128 t3 = (u128)hi * r0;
+        const u64 tmp1b = tmp1 + (u64)t3;
+        carry = (u64)(t3 >> 64) + (tmp1b < tmp1);
+        const u64 qe = hi * r1 + tmp3 + carry;
+        const u64 r = lo - qe * q;
+        return r >= q ? r - q : r;
+    }
+    inline u64 mul(u64 a, u64 b) const
+    {
+        const u128 p = (u128)a * b;
+        return red128((u64)(p >> 64), (u64)p);
+    }
+    // a * b + c mod q (a, b, c < 2^63)
+    inline u64 mad(u64 a, u64 b, u64 c) const
+    {
+        const u128 p = (u128)a * b + c;
+        return red128((u64)(p >> 64), (u64)p);
+    }
+    // x mod q for any 64-bit x
+    inline u64 red64(u64 x) const
+    {
+        const u64 r = x - (u64)(((u128)x * r1) >> 64) * q;
+        return r >= q ? r - q : r;
+    }
+};
 static inline uint32_t brv(uint32_t x, int bits)
 {
     uint32_t r = 0;
     for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
     return r;
+}
+
+// self-check of FastMod against the plain `%` forms on n pseudo-random operand triples (and the extreme operands);
+// returns the number of mismatches
+extern "C" size_t orc_selftest_fastmod(uint64_t q, size_t n, uint64_t seed)
+{
+    FastMod fm;
+    fm.init(q);
+    size_t bad = 0;
+    u64 s = seed | 1;
+    auto next = [&]() {   // xorshift64*
+        s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+        return s * 0x2545F4914F6CDD1Dull;
+    };
+    auto check = [&](u64 a, u64 b, u64 c, u64 x) {
+        if (fm.mul(a, b) != mulmod(a, b, q)) bad++;
+        if (fm.mad(a, b, c) != (u64)(((u128)a * b + c) % q)) bad++;
+        if (fm.red64(x) != x % q) bad++;
+        if (fm.red128(x, a) != (u64)((((u128)x << 64) | a) % q)) bad++;
+    };
+    const u64 ext[] = { 0, 1, q - 1, q >> 1, (q >> 1) + 1 };
+    for (u64 a : ext)
+        for (u64 b : ext)
+            for (u64 c : ext) check(a, b, c, ~u64(0) - a);
+    for (size_t i = 0; i < n; i++) check(next() % q, next() % q, next() % q, next());
+    return bad;
 }
 
 // ------------------------------------------------------------------ number theory
@@ -206,9 +278,11 @@ struct Limb {
     u64 q = 0, psi = 0;
     std::vector<u64> rp, rps, irp, irps;   // rp[k] = psi^{brv(k)}, irp[k] = rp[k]^{-1}; *s = Shoup quotients
     u64 ninv = 0, ninvs = 0;
+    FastMod fm;
     void init(u64 q_, size_t N, int logn)
     {
         q = q_;
+        fm.init(q_);
         orc_minimal_primitive_root(2 * N, q, &psi);
         rp.assign(N, 0); rps.assign(N, 0); irp.assign(N, 0); irps.assign(N, 0);
         u64 ipsi = invmod_prime(psi, q);
@@ -230,10 +304,15 @@ struct Conv {
     std::vector<u64> ib, ob;
     std::vector<u64> inv_punct;              // (prod ib / ib_i)^{-1} mod ib_i
     std::vector<std::vector<u64>> mat;       // mat[o][i] = (prod ib / ib_i) mod ob_o
+    std::vector<FastMod> fib, fob;
     void init(const std::vector<u64> &ibase, const std::vector<u64> &obase)
     {
         ib = ibase; ob = obase;
         size_t n = ib.size();
+        fib.resize(n);
+        for (size_t i = 0; i < n; i++) fib[i].init(ib[i]);
+        fob.resize(ob.size());
+        for (size_t o = 0; o < ob.size(); o++) fob[o].init(ob[o]);
         inv_punct.resize(n);
         for (size_t i = 0; i < n; i++) {
             u64 p = 1;
@@ -256,12 +335,12 @@ struct Conv {
         size_t n = ib.size();
         std::vector<u64> tmp(n * N);
         for (size_t i = 0; i < n; i++)
-            for (size_t c = 0; c < N; c++) tmp[i * N + c] = mulmod(in[i * N + c] % ib[i], inv_punct[i], ib[i]);
+            for (size_t c = 0; c < N; c++) tmp[i * N + c] = fib[i].mul(fib[i].red64(in[i * N + c]), inv_punct[i]);
         for (size_t o = 0; o < ob.size(); o++)
             for (size_t c = 0; c < N; c++) {
-                u128 acc = 0;   // n <= ~12 terms of < 2^122: reduce as we go
-                for (size_t i = 0; i < n; i++) acc = (acc + (u128)tmp[i * N + c] * mat[o][i]) % ob[o];
-                out[o * N + c] = (u64)acc;
+                u64 acc = 0;   // reduce as we go
+                for (size_t i = 0; i < n; i++) acc = fob[o].mad(tmp[i * N + c], mat[o][i], acc);
+                out[o * N + c] = acc;
             }
     }
 };
@@ -324,6 +403,7 @@ static void init_behz(orc_ctx *c)
     c->q_to_mtilde.ib = q;
     c->q_to_mtilde.ob = { c->m_tilde };
     c->q_to_mtilde.inv_punct = c->q_to_bsk.inv_punct;
+    c->q_to_mtilde.fib = c->q_to_bsk.fib;
     c->q_to_mtilde.mat.assign(1, std::vector<u64>(L));
     for (size_t i = 0; i < L; i++) {
         u64 p = 1;
@@ -373,6 +453,9 @@ extern "C" orc_ctx *orc_ctx_create(int scheme, size_t N, size_t K, const uint64_
 }
 extern "C" void orc_ctx_destroy(orc_ctx *c) { delete c; }
 extern "C" uint64_t orc_ctx_psi(const orc_ctx *c, size_t limb) { return c->limbs[limb].psi; }
+extern "C" size_t orc_ctx_N(const orc_ctx *c) { return c->N; }
+extern "C" size_t orc_ctx_K(const orc_ctx *c) { return c->K; }
+extern "C" int orc_ctx_scheme(const orc_ctx *c) { return c->scheme; }
 extern "C" size_t orc_ctx_bsk_size(const orc_ctx *c) { return c->bsk.size(); }
 extern "C" void orc_ctx_bsk(const orc_ctx *c, uint64_t *out)
 {
@@ -475,13 +558,13 @@ extern "C" void orc_ckks_multiply(const orc_ctx *c, size_t L, const uint64_t *a,
 {
     size_t N = c->N;
     for (size_t l = 0; l < L; l++) {
-        u64 q = c->limbs[l].q;
+        const FastMod &fm = c->limbs[l].fm;
         const u64 *a0 = a + l * N, *a1 = a + (L + l) * N, *b0 = b + l * N, *b1 = b + (L + l) * N;
         u64 *c0 = out + l * N, *c1 = out + (L + l) * N, *c2 = out + (2 * L + l) * N;
         for (size_t j = 0; j < N; j++) {
-            c0[j] = mulmod(a0[j], b0[j], q);
-            c1[j] = addmod(mulmod(a0[j], b1[j], q), mulmod(a1[j], b0[j], q), q);
-            c2[j] = mulmod(a1[j], b1[j], q);
+            c0[j] = fm.mul(a0[j], b0[j]);
+            c1[j] = fm.mad(a0[j], b1[j], fm.mul(a1[j], b0[j]));
+            c2[j] = fm.mul(a1[j], b1[j]);
         }
     }
 }
@@ -498,9 +581,9 @@ extern "C" void orc_multiply_plain(const orc_ctx *c, size_t L, size_t size, cons
     size_t N = c->N;
     for (size_t p = 0; p < size; p++)
         for (size_t l = 0; l < L; l++) {
-            u64 q = c->limbs[l].q;
+            const FastMod &fm = c->limbs[l].fm;
             size_t o = (p * L + l) * N;
-            for (size_t j = 0; j < N; j++) out[o + j] = mulmod(ct[o + j], pl[l * N + j], q);
+            for (size_t j = 0; j < N; j++) out[o + j] = fm.mul(ct[o + j], pl[l * N + j]);
         }
 }
 // add_plain_inplace (CKKS): R/src/engine/seal_context.cpp:454
@@ -536,14 +619,16 @@ extern "C" void orc_switch_key(const orc_ctx *c, size_t L, uint64_t *ct, const u
                 op = target + J * N;
             } else {
                 const u64 qj = c->limbs[J].q;
-                for (size_t n = 0; n < N; n++) d[n] = (qj > qi) ? t[J * N + n] % qi : t[J * N + n];
+                const FastMod &fi = c->limbs[ki].fm;
+                for (size_t n = 0; n < N; n++) d[n] = (qj > qi) ? fi.red64(t[J * N + n]) : t[J * N + n];
                 ntt_fwd(c->limbs[ki], N, d.data());
                 op = d.data();
             }
             for (size_t k = 0; k < 2; k++) {
                 const u64 *kp = key + ((J * 2 + k) * K + ki) * N;
                 u64 *ap = acc.data() + (k * (L + 1) + I) * N;
-                for (size_t n = 0; n < N; n++) ap[n] = addmod(ap[n], mulmod(op[n], kp[n], qi), qi);
+                const FastMod &fi = c->limbs[ki].fm;
+                for (size_t n = 0; n < N; n++) ap[n] = fi.mad(op[n], kp[n], ap[n]);
             }
         }
     }
@@ -552,20 +637,21 @@ extern "C" void orc_switch_key(const orc_ctx *c, size_t L, uint64_t *ct, const u
     for (size_t k = 0; k < 2; k++) {
         u64 *last = acc.data() + (k * (L + 1) + L) * N;
         ntt_inv(c->limbs[sp], N, last);
-        for (size_t n = 0; n < N; n++) last[n] = (last[n] + half) % qk;
+        for (size_t n = 0; n < N; n++) last[n] = addmod(last[n], half, qk);
         for (size_t J = 0; J < L; J++) {
             const u64 qj = c->limbs[J].q;
             const u64 fix = qj - half % qj;
             const u64 inv = invmod_prime(qk % qj, qj);
             u64 *aj = acc.data() + (k * (L + 1) + J) * N;
-            for (size_t n = 0; n < N; n++) d[n] = (last[n] % qj + fix) % qj;
+            const FastMod &fj = c->limbs[J].fm;
+            for (size_t n = 0; n < N; n++) d[n] = addmod(fj.red64(last[n]), fix % qj, qj);
             if (ckks)
                 ntt_fwd(c->limbs[J], N, d.data());
             else
                 ntt_inv(c->limbs[J], N, aj);
             u64 *dst = ct + (k * L + J) * N;
             for (size_t n = 0; n < N; n++) {
-                u64 v = mulmod(submod(aj[n], d[n], qj), inv, qj);
+                u64 v = fj.mul(submod(aj[n], d[n], qj), inv);
                 dst[n] = addmod(dst[n], v, qj);
             }
         }
@@ -657,16 +743,17 @@ extern "C" void orc_rescale(const orc_ctx *c, size_t L, size_t size, const uint6
     for (size_t p = 0; p < size; p++) {
         memcpy(last.data(), in + (p * L + L - 1) * N, N * sizeof(u64));
         if (ckks) ntt_inv(c->limbs[L - 1], N, last.data());
-        for (size_t n = 0; n < N; n++) last[n] = (last[n] + half) % ql;
+        for (size_t n = 0; n < N; n++) last[n] = addmod(last[n], half, ql);
         for (size_t i = 0; i + 1 < L; i++) {
             const u64 qi = c->limbs[i].q;
             const u64 fix = qi - half % qi;
             const u64 inv = invmod_prime(ql % qi, qi);
-            for (size_t n = 0; n < N; n++) d[n] = (last[n] % qi + fix) % qi;
+            const FastMod &fi = c->limbs[i].fm;
+            for (size_t n = 0; n < N; n++) d[n] = addmod(fi.red64(last[n]), fix % qi, qi);
             if (ckks) ntt_fwd(c->limbs[i], N, d.data());
             const u64 *src = in + (p * L + i) * N;
             u64 *dst = out + (p * (L - 1) + i) * N;
-            for (size_t n = 0; n < N; n++) dst[n] = mulmod(submod(src[n], d[n], qi), inv, qi);
+            for (size_t n = 0; n < N; n++) dst[n] = fi.mul(submod(src[n], d[n], qi), inv);
         }
     }
 }
@@ -683,7 +770,8 @@ static void behz_extend(const orc_ctx *c, const u64 *x /*[L][N] coeff form*/, u6
     std::vector<u64> tmp(L * N), tb((nb + 1) * N);
     for (size_t l = 0; l < L; l++) {
         u64 q = c->limbs[l].q, mt = c->m_tilde % q;
-        for (size_t n = 0; n < N; n++) tmp[l * N + n] = mulmod(x[l * N + n], mt, q);
+        const FastMod &fm = c->limbs[l].fm;
+        for (size_t n = 0; n < N; n++) tmp[l * N + n] = fm.mul(x[l * N + n], mt);
     }
     c->q_to_bsk.convert(tmp.data(), tb.data(), N);
     {   // to m_tilde = 2^32
@@ -691,7 +779,7 @@ static void behz_extend(const orc_ctx *c, const u64 *x /*[L][N] coeff form*/, u6
         for (size_t n = 0; n < N; n++) {
             u64 acc = 0;
             for (size_t l = 0; l < L; l++) {
-                u64 v = mulmod(tmp[l * N + n], cv.inv_punct[l], cv.ib[l]);
+                u64 v = cv.fib[l].mul(tmp[l * N + n], cv.inv_punct[l]);
                 acc += v * cv.mat[0][l];   // mod 2^64, then masked
             }
             tb[nb * N + n] = acc & 0xffffffffull;
@@ -704,8 +792,8 @@ static void behz_extend(const orc_ctx *c, const u64 *x /*[L][N] coeff form*/, u6
         for (size_t n = 0; n < N; n++) {
             u64 r = (tb[nb * N + n] * c->neg_inv_prod_q_mod_mtilde) & 0xffffffffull;
             if (r >= mt_half) r += p - mt;
-            u64 v = (u64)(((u128)r * pq + tb[i * N + n]) % p);
-            xb[i * N + n] = mulmod(v, imt, p);
+            u64 v = c->bsk[i].fm.mad(r, pq, tb[i * N + n]);
+            xb[i * N + n] = c->bsk[i].fm.mul(v, imt);
         }
     }
     for (size_t i = 0; i < nb; i++) ntt_fwd(c->bsk[i], N, xb + i * N);
@@ -723,13 +811,13 @@ extern "C" void orc_bfv_multiply(const orc_ctx *c, const uint64_t *a, const uint
     auto tensor = [&](const std::vector<u64> &x, const std::vector<u64> &y, std::vector<u64> &d, size_t nl,
                       const std::vector<Limb> &base) {
         for (size_t l = 0; l < nl; l++) {
-            const u64 q = base[l].q;
+            const FastMod &fm = base[l].fm;
             const u64 *x0 = &x[l * N], *x1 = &x[(nl + l) * N], *y0 = &y[l * N], *y1 = &y[(nl + l) * N];
             u64 *d0 = &d[l * N], *d1 = &d[(nl + l) * N], *d2 = &d[(2 * nl + l) * N];
             for (size_t n = 0; n < N; n++) {
-                d0[n] = mulmod(x0[n], y0[n], q);
-                d1[n] = addmod(mulmod(x0[n], y1[n], q), mulmod(x1[n], y0[n], q), q);
-                d2[n] = mulmod(x1[n], y1[n], q);
+                d0[n] = fm.mul(x0[n], y0[n]);
+                d1[n] = fm.mad(x0[n], y1[n], fm.mul(x1[n], y0[n]));
+                d2[n] = fm.mul(x1[n], y1[n]);
             }
             ntt_inv(base[l], N, d0);
             ntt_inv(base[l], N, d1);
@@ -743,34 +831,35 @@ extern "C" void orc_bfv_multiply(const orc_ctx *c, const uint64_t *a, const uint
         // (6) multiply by t
         for (size_t l = 0; l < L; l++) {
             u64 q = c->limbs[l].q;
-            for (size_t n = 0; n < N; n++) tq[l * N + n] = mulmod(dq[(p * L + l) * N + n], c->t % q, q);
+            for (size_t n = 0; n < N; n++) tq[l * N + n] = c->limbs[l].fm.mul(dq[(p * L + l) * N + n], c->t % q);
         }
         for (size_t i = 0; i < nb; i++) {
             u64 q = c->bsk[i].q;
-            for (size_t n = 0; n < N; n++) tb[i * N + n] = mulmod(db[(p * nb + i) * N + n], c->t % q, q);
+            for (size_t n = 0; n < N; n++) tb[i * N + n] = c->bsk[i].fm.mul(db[(p * nb + i) * N + n], c->t % q);
         }
         // (7) fast_floor: (y_p - conv_{q->p}(y_q)) * q^{-1} mod p
         c->q_to_bsk.convert(tq.data(), conv.data(), N);
         for (size_t i = 0; i < nb; i++) {
             u64 q = c->bsk[i].q;
             for (size_t n = 0; n < N; n++)
-                fl[i * N + n] = mulmod(submod(tb[i * N + n], conv[i * N + n], q), c->inv_prod_q_mod_bsk[i], q);
+                fl[i * N + n] = c->bsk[i].fm.mul(submod(tb[i * N + n], conv[i * N + n], q), c->inv_prod_q_mod_bsk[i]);
         }
         // (8) fastbconv_sk: Shenoy-Kumaresan Bsk -> q
         c->B_to_q.convert(fl.data(), outq.data(), N);
         c->B_to_msk.convert(fl.data(), sk.data(), N);
         const u64 msk = c->m_sk, msk_half = msk >> 1;
         for (size_t n = 0; n < N; n++)
-            sk[n] = mulmod(submod(sk[n], fl[nB * N + n], msk), c->inv_prod_B_mod_msk, msk);
+            sk[n] = c->bsk[nB].fm.mul(submod(sk[n], fl[nB * N + n], msk), c->inv_prod_B_mod_msk);
         for (size_t l = 0; l < L; l++) {
             const u64 q = c->limbs[l].q, pB = c->prod_B_mod_q[l];
             u64 *dst = out + (p * L + l) * N;
             for (size_t n = 0; n < N; n++) {
                 u64 al = sk[n];
+                const FastMod &fm = c->limbs[l].fm;
                 if (al > msk_half)
-                    dst[n] = (u64)(((u128)((msk - al) % q) * pB + outq[l * N + n]) % q);
+                    dst[n] = fm.mad(fm.red64(msk - al), pB, outq[l * N + n]);
                 else
-                    dst[n] = (u64)(((u128)(al % q) * (q - pB) + outq[l * N + n]) % q);
+                    dst[n] = fm.mad(fm.red64(al), q - pB, outq[l * N + n]);
             }
         }
     }

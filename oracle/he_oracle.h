@@ -55,6 +55,9 @@ void orc_galois_table_ntt(size_t N, uint32_t elt, uint32_t *table);
 orc_ctx *orc_ctx_create(int scheme, size_t N, size_t K, const uint64_t *moduli, uint64_t plain_modulus);
 void orc_ctx_destroy(orc_ctx *c);
 uint64_t orc_ctx_psi(const orc_ctx *c, size_t limb);
+size_t orc_ctx_N(const orc_ctx *c);
+size_t orc_ctx_K(const orc_ctx *c);
+int orc_ctx_scheme(const orc_ctx *c);
 /* number of BEHZ auxiliary primes |Bsk| (BFV only) and their values (Bsk..., m_sk last) */
 size_t orc_ctx_bsk_size(const orc_ctx *c);
 void orc_ctx_bsk(const orc_ctx *c, uint64_t *out);
@@ -105,6 +108,31 @@ int orc_batch_dot(const orc_ctx *c, size_t L, size_t n, const uint64_t *a, const
 /* batched single-limb forward NTTs (for the NTT limb-ops/s baseline) */
 void orc_batch_ntt(const orc_ctx *c, size_t limb, size_t n, uint64_t *polys, int inverse, int threads);
 int orc_max_threads(void);
+/* Barrett fast path of the hot loops vs the plain 128-bit `%` forms: number of mismatches over n random triples */
+size_t orc_selftest_fastmod(uint64_t q, size_t n, uint64_t seed);
+
+/* ---- workload bodies (he_oracle_workloads.cpp): the reference's operate() bodies and the composite helpers of
+ *      R/src/engine/seal_context.cpp:255-458, fed the same input and injected fresh encryptions as the plugin; they
+ *      check the ciphertexts store() returns, bit for bit.  Layouts: ciphertext arrays [count][size][L][N]. ---- */
+/* MatMultVal (R/src/benchmarks/ckks/seal_ckks_matmultval_benchmark.cpp:235-270): out [r0*c1][2][Lout][N], Lout = L-1 CKKS / L BFV */
+int orc_matmul_val(const orc_ctx *c, size_t L, size_t r0, size_t c0, size_t c1, const uint64_t *m0, const uint64_t *m1t,
+                   const uint64_t *relin, const uint32_t *elts, const uint64_t *const *gal, size_t ngal, uint64_t *out, int threads);
+/* MatMultRow (R/src/benchmarks/ckks/seal_ckks_matmult_row_benchmark.cpp:472-523): out [nA][2][L][N] */
+int orc_matmul_row(const orc_ctx *c, size_t L, size_t nA, size_t dim2, int spacers, const uint64_t *A, const uint64_t *B,
+                   const uint64_t *relin, const uint32_t *elts, const uint64_t *const *gal, size_t ngal, uint64_t *out, int threads);
+/* MatMult CipherBatchAxis (R/src/benchmarks/ckks/seal_ckks_matmult_cipherbatchaxis_benchmark.cpp:385-441) */
+int orc_matmul_cba(const orc_ctx *c, size_t L, size_t r0, size_t c0, size_t c1, const uint64_t *m0, const uint64_t *m1,
+                   const uint64_t *relin, uint64_t *out, int threads);
+/* collapseCKKS (R/src/engine/seal_context.cpp:349-415): out [2][L-1][N] */
+int orc_collapse(const orc_ctx *c, size_t L, size_t n, const uint64_t *cts, size_t first_index, const uint64_t *masks,
+                 const uint64_t *zero_ct, const uint32_t *elts, const uint64_t *const *gal, size_t ngal, uint64_t *out, int threads);
+/* evaluatePolynomial (R/src/engine/seal_context.cpp:417-458): returns the level of out (> 0) or an error (< 0) */
+int orc_horner(const orc_ctx *c, size_t Lx, const uint64_t *x, const uint64_t *seed, size_t ncoef, const uint64_t *coeffs,
+               const uint64_t *relin, uint64_t *out);
+/* LogRegHornerBenchmark::operate (R/src/benchmarks/ckks/seal_ckks_logreg_horner.cpp:388-481): returns the level of out */
+int orc_logreg(const orc_ctx *c, size_t n_features, size_t batch, const uint64_t *W, const uint64_t *b, const uint64_t *X,
+               const uint64_t *masks, const uint64_t *zero_ct, const uint64_t *seed, size_t ncoef, const uint64_t *coeffs,
+               const uint64_t *relin, const uint32_t *elts, const uint64_t *const *gal, size_t ngal, uint64_t *out, int threads);
 
 #ifdef __cplusplus
 }

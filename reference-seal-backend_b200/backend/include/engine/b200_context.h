@@ -66,6 +66,14 @@ public:
     std::vector<std::uint64_t> partition(std::uint64_t n) const;
     // every call into libb200he goes through check(): a non-zero return becomes HEBenchError(HEBSEAL_ECODE_SEAL_ERROR)
     void check(int rc, const char *what) const;
+    // Diagnostic trace (off unless HEB_B200_TRACE_DIR names a directory): the ciphertexts that cross load() / store() and
+    // the fresh encryptions drawn inside operate() (R/src/engine/seal_context.cpp:360,440) are written to <dir>/<tag>.bin
+    // (header: 8 x u64 = magic "B200TRC1", items written, size, L, N, ntt form, scale as IEEE bits, items in the vector; then the
+    // uint64 data; HEB_B200_TRACE_PICK_<tag>="i,j,..." restricts a tag to those items).
+    // tests/test_workload_parity.py replays them through the CPU oracle's workload bodies and compares bit for bit.
+    bool tracing() const { return !m_trace_dir.empty(); }
+    void trace(const std::string &tag, const std::vector<Ciphertext> &v) const;
+    void trace(const std::string &tag, const Ciphertext &c) const { trace(tag, std::vector<Ciphertext>(1, c)); }
 
     // composite operations of R/src/engine/seal_context.cpp:255-458, on device batches
     void matchLevel(DeviceBatch &a, DeviceBatch &b) const;
@@ -86,9 +94,9 @@ private:
     double m_scale   = 1.0;
     std::uint64_t m_t = 0;
     hfhe_ctx *m_host  = nullptr;
-    mutable std::mutex m_host_mtx;   // the host stand-in's PRNG is not thread safe
     std::vector<b200he_ctx *> m_dev;
     std::vector<int> m_dev_of_ctx;
+    std::string m_trace_dir;
     std::map<std::string, DeviceBatchPtr> m_mask_cache;   // collapse masks per (gpu, first, n, total, level)
 };
 

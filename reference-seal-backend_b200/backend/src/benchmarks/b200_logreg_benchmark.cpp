@@ -145,6 +145,9 @@ Handle LogRegHornerBenchmark::load(const Handle *p_local_data, std::uint64_t cou
     SEALContextWrapper &cw       = *m_p_ctx_wrapper;
     LoadedOpParams loaded;
     const std::vector<Ciphertext> &X = std::get<2>(enc);
+    cw.trace("W", std::get<0>(enc));
+    cw.trace("b", std::get<1>(enc));
+    cw.trace("X", X);
     loaded.X.first                   = cw.partition(X.size());
     for (int g = 0; g < cw.gpuCount(); ++g) {
         loaded.W.push_back(cw.upload(g, std::get<0>(enc)));
@@ -160,6 +163,7 @@ void LogRegHornerBenchmark::store(Handle remote_data, Handle *p_local_data, std:
         std::memset(p_local_data, 0, sizeof(Handle) * count);
         const DeviceBatchPtr &res = this->getEngine().retrieveFromHandle<DeviceBatchPtr>(remote_data, EncryptedResultTag);
         std::vector<Ciphertext> h = m_p_ctx_wrapper->download(*res);
+        m_p_ctx_wrapper->trace("out", h);
         p_local_data[0]           = this->getEngine().createHandle<Ciphertext>(sizeof(Ciphertext), EncryptedResultTag, std::move(h.at(0)));
     }
 }

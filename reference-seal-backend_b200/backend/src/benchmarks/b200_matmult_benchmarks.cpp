@@ -78,7 +78,9 @@ template <bool CKKS> std::vector<Plaintext> MatMultBenchmarkT<CKKS>::encodeM0(co
     if (m_algo == MatMultAlgo::Val) {   // one row per plaintext
         for (std::size_t i = 0; i < r0; ++i) out.push_back(cw.encodeVector(std::vector<Scalar>(m + i * c0, m + (i + 1) * c0)));
     } else if (m_algo == MatMultAlgo::CipherBatchAxis) {   // one element per plaintext, broadcast to every slot; row-major
-        for (std::size_t i = 0; i < r0 * c0; ++i) out.push_back(cw.encodeVector(std::vector<Scalar>(cw.slotCount(), m[i])));
+        out.resize(r0 * c0);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long i = 0; i < (long)(r0 * c0); ++i) out[i] = cw.encodeVector(std::vector<Scalar>(cw.slotCount(), m[i]));
     } else if (CKKS) {   // Row: slot[spacers*j + k] = M0[i][j] for k < cols_M1 (…ckks_matmult_row…:234-244)
         const std::size_t spacers = cw.slotCount() / c0;
         for (std::size_t i = 0; i < r0; ++i) {
@@ -114,7 +116,9 @@ template <bool CKKS> std::vector<Plaintext> MatMultBenchmarkT<CKKS>::encodeM1(co
             out.push_back(cw.encodeVector(col));
         }
     } else if (m_algo == MatMultAlgo::CipherBatchAxis) {
-        for (std::size_t i = 0; i < c0 * c1; ++i) out.push_back(cw.encodeVector(std::vector<Scalar>(cw.slotCount(), m[i])));
+        out.resize(c0 * c1);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long i = 0; i < (long)(c0 * c1); ++i) out[i] = cw.encodeVector(std::vector<Scalar>(cw.slotCount(), m[i]));
     } else {   // Row: slot[spacers*j + k] = M1[j][k]; BFV repeats it in the second batching row
         const std::size_t row_size = CKKS ? cw.slotCount() : cw.slotCount() / 2, spacers = row_size / c0;
         std::vector<Scalar> v(cw.slotCount(), 0);
@@ -155,6 +159,8 @@ template <bool CKKS> Handle MatMultBenchmarkT<CKKS>::load(const Handle *p_local_
 {
     if (count != 1) throw HEBenchError(HEBERROR_MSG_CLASS("Expected only 1 local handle to load."), HEBENCH_ECODE_INVALID_ARGS);
     const EncryptedMats &enc = this->getEngine().template retrieveFromHandle<EncryptedMats>(p_local_data[0]);
+    m_p_ctx_wrapper->trace("in0", enc[0]);
+    m_p_ctx_wrapper->trace("in1", enc[1]);
     LoadedMats loaded        = { replicate(*m_p_ctx_wrapper, enc[0]), replicate(*m_p_ctx_wrapper, enc[1]) };
     return this->getEngine().template createHandle<LoadedMats>(sizeof(LoadedMats), 0, std::move(loaded));
 }
@@ -165,6 +171,7 @@ template <bool CKKS> void MatMultBenchmarkT<CKKS>::store(Handle remote_data, Han
         std::memset(p_local_data, 0, sizeof(Handle) * count);
         const ShardedCiphertexts &res = this->getEngine().template retrieveFromHandle<ShardedCiphertexts>(remote_data, ResultCipherTag);
         std::vector<Ciphertext> host  = gather(*m_p_ctx_wrapper, res);
+        m_p_ctx_wrapper->trace("out", host);
         p_local_data[0] = this->getEngine().template createHandle<std::vector<Ciphertext>>(sizeof(host), ResultCipherTag, std::move(host));
     }
 }

@@ -230,7 +230,10 @@ template <bool CKKS> Handle VectorBenchmarkT<CKKS>::load(const Handle *p_local_d
     const EncryptedParams &enc = this->getEngine().template retrieveFromHandle<EncryptedParams>(p_local_data[0]);
     if (enc.size() != 2) throw HEBenchError(HEBERROR_MSG_CLASS("Expected 2 operation parameters."), HEBENCH_ECODE_INVALID_ARGS);
     LoadedParams loaded;
-    for (int p = 0; p < 2; ++p) loaded[p] = replicate(*m_p_ctx_wrapper, enc[p]);
+    for (int p = 0; p < 2; ++p) {
+        m_p_ctx_wrapper->trace(p ? "in1" : "in0", enc[p]);
+        loaded[p] = replicate(*m_p_ctx_wrapper, enc[p]);
+    }
     return this->getEngine().template createHandle<LoadedParams>(sizeof(LoadedParams), 0, std::move(loaded));
 }
 
@@ -241,6 +244,7 @@ template <bool CKKS> void VectorBenchmarkT<CKKS>::store(Handle remote_data, Hand
         std::memset(p_local_data, 0, sizeof(Handle) * count);
         const ShardedCiphertexts &res = this->getEngine().template retrieveFromHandle<ShardedCiphertexts>(remote_data);
         std::vector<Ciphertext> host  = gather(*m_p_ctx_wrapper, res);
+        m_p_ctx_wrapper->trace("out", host);
         p_local_data[0]               = this->getEngine().template createHandle<std::vector<Ciphertext>>(sizeof(host), 0, std::move(host));
     }
 }

@@ -4,7 +4,9 @@
 #include "engine/b200_context.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <sstream>
 
 #include "../../hostfhe/hostfhe.h"
@@ -49,7 +51,10 @@ void SEALContextWrapper::init(bool ckks, std::size_t N, std::size_t depth, int c
     m_N          = N;
     m_K          = depth + 1;
     m_scale_bits = scale_or_plain_bits;
-    std::uint64_t seed = 0x9e3779b97f4a7c15ull;
+    if (const char *e = getenv("HEB_B200_TRACE_DIR")) m_trace_dir = e;
+    // key material and encryption randomness come from OS entropy (seed 0) unless HEB_B200_SEED fixes them: reproducible
+    // keys and encryptions are for the parity tests and benchmarks only
+    std::uint64_t seed = 0;
     if (const char *e = getenv("HEB_B200_SEED")) seed = strtoull(e, nullptr, 0);
     m_host = hfhe_create(ckks ? HFHE_CKKS : HFHE_BFV, N, depth, coeff_bits, scale_or_plain_bits, seed);
     if (!m_host) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Invalid encryption parameters."), HEBSEAL_ECODE_SEAL_ERROR);
@@ -135,15 +140,25 @@ Ciphertext SEALContextWrapper::encrypt(const Plaintext &plain)
     c.ntt   = m_ckks;
     c.scale = m_ckks ? plain.scale : 1.0;
     c.data.resize(2 * topLevel() * m_N);
-    std::lock_guard<std::mutex> lock(m_host_mtx);
-    hfhe_encrypt(m_host, plain.data.data(), c.data.data());
+    hfhe_encrypt(m_host, plain.data.data(), c.data.data());   // thread safe: one keystream per encryption
     return c;
 }
+// every encryption of the vector draws from its own keystream (index reserved up front, so a fixed seed gives the
+// same bits whatever the thread schedule): the vector is encrypted on all host threads
 std::vector<Ciphertext> SEALContextWrapper::encrypt(const std::vector<Plaintext> &plain)
 {
-    std::vector<Ciphertext> out;
-    out.reserve(plain.size());
-    for (const Plaintext &p : plain) out.push_back(encrypt(p));
+    std::vector<Ciphertext> out(plain.size());
+    const std::uint64_t first = hfhe_reserve_encryptions(m_host, plain.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long i = 0; i < (long)plain.size(); ++i) {
+        Ciphertext &c = out[i];
+        c.size        = 2;
+        c.L           = (int)topLevel();
+        c.ntt         = m_ckks;
+        c.scale       = m_ckks ? plain[i].scale : 1.0;
+        c.data.resize(2 * topLevel() * m_N);
+        hfhe_encrypt_at(m_host, plain[i].data.data(), c.data.data(), first + (std::uint64_t)i);
+    }
     return out;
 }
 Plaintext SEALContextWrapper::decrypt(const Ciphertext &cipher)
@@ -157,10 +172,47 @@ Plaintext SEALContextWrapper::decrypt(const Ciphertext &cipher)
 }
 std::vector<Plaintext> SEALContextWrapper::decrypt(const std::vector<Ciphertext> &cipher)
 {
-    std::vector<Plaintext> out;
-    out.reserve(cipher.size());
-    for (const Ciphertext &c : cipher) out.push_back(decrypt(c));
+    std::vector<Plaintext> out(cipher.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long i = 0; i < (long)cipher.size(); ++i) out[i] = decrypt(cipher[i]);   // read-only on the host context
     return out;
+}
+
+void SEALContextWrapper::trace(const std::string &tag, const std::vector<Ciphertext> &v) const
+{
+    if (m_trace_dir.empty()) return;
+    // HEB_B200_TRACE_PICK_<tag> = "i,j,k,...": write only those items (full-shape runs trace a few result cells and the
+    // operands they depend on instead of gigabytes)
+    std::vector<std::size_t> pick;
+    if (const char *e = getenv(("HEB_B200_TRACE_PICK_" + tag).c_str())) {
+        for (const char *p = e; *p;) {
+            char *end            = nullptr;
+            const std::size_t id = strtoull(p, &end, 10);
+            if (end == p) break;
+            if (id < v.size()) pick.push_back(id);
+            p = *end ? end + 1 : end;
+        }
+    } else
+        for (std::size_t i = 0; i < v.size(); ++i) pick.push_back(i);
+    const std::string path = m_trace_dir + "/" + tag + ".bin";
+    FILE *f                = fopen(path.c_str(), "wb");
+    if (!f) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("HEB_B200_TRACE_DIR: cannot write " + path), HEBENCH_ECODE_CRITICAL_ERROR);
+    std::uint64_t hdr[8] = { 0x3143525430303242ull /* "B200TRC1" */, pick.size(), 0, 0, m_N, 0, 0, v.size() };
+    if (!pick.empty()) {
+        const Ciphertext &c0 = v[pick[0]];
+        hdr[2]               = (std::uint64_t)c0.size;
+        hdr[3]               = (std::uint64_t)c0.L;
+        hdr[5]               = c0.ntt ? 1 : 0;
+        std::memcpy(&hdr[6], &c0.scale, sizeof(double));
+    }
+    bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1;
+    for (std::size_t id : pick) {
+        const Ciphertext &c = v[id];
+        if (c.size != v[pick[0]].size || c.L != v[pick[0]].L) ok = false;   // one shape per file
+        ok = ok && fwrite(c.data.data(), sizeof(std::uint64_t), c.data.size(), f) == c.data.size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("HEB_B200_TRACE_DIR: short write to " + path), HEBENCH_ECODE_CRITICAL_ERROR);
 }
 
 // ------------------------------------------------------------------ device side
@@ -301,7 +353,9 @@ DeviceBatchPtr SEALContextWrapper::collapseCKKS(DeviceBatch &ciphers, std::size_
     if (add_encrypted_zero) {
         // retval = Enc(0) at the top level, switched down to the summands' level, scale forced (:360-361, :397-400)
         Plaintext zero = encodeVector(std::vector<double>(1, 0.0), m_scale);
-        DeviceBatchPtr z = upload(g, encrypt(zero));
+        const Ciphertext zc = encrypt(zero);
+        trace("collapse_zero", zc);
+        DeviceBatchPtr z = upload(g, zc);
         if (n > 0) {
             check(b200he_mod_drop(c, z->get(), result->level(), z->get()), "b200he_mod_drop");
             check(b200he_batch_set_scale(z->get(), result->scale()), "b200he_batch_set_scale");
@@ -322,7 +376,9 @@ DeviceBatchPtr SEALContextWrapper::evaluatePolynomial(DeviceBatch &cipher_input,
     for (std::size_t i = 0; i < m_dev.size(); ++i)
         if (m_dev[i] == c) g = (int)i;
     auto it = plain_coefficients.rbegin();
-    DeviceBatchPtr retval = upload(g, encrypt(*it));
+    const Ciphertext seed = encrypt(*it);
+    trace("horner_seed", seed);
+    DeviceBatchPtr retval = upload(g, seed);
     for (++it; it != plain_coefficients.rend(); ++it) {
         matchLevel(cipher_input, *retval);
         check(b200he_multiply(c, retval->get(), nullptr, cipher_input.get(), nullptr, 1, retval->get()), "b200he_multiply");

@@ -3,8 +3,12 @@
 // (R/src/engine/seal_context.cpp:46-70).  No Evaluator arithmetic lives here.
 #include "hostfhe.h"
 
+#include <sys/random.h>
+
+#include <atomic>
 #include <cmath>
 #include <complex>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -192,22 +196,60 @@ struct Big {
     }
 };
 
-struct Rng {   // xoshiro256**
-    u64 s[4];
-    explicit Rng(u64 seed)
-    {
-        for (int i = 0; i < 4; i++) {   // splitmix64
-            u64 z = (seed += 0x9e3779b97f4a7c15ull);
-            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-            s[i] = z ^ (z >> 31);
-        }
+bool os_entropy(void *dst, size_t n)
+{
+    unsigned char *p = (unsigned char *)dst;
+    size_t got = 0;
+    while (got < n) {
+        ssize_t r = getrandom(p + got, n - got, 0);
+        if (r <= 0) break;
+        got += (size_t)r;
     }
-    static u64 rotl(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
+    if (got == n) return true;
+    FILE *f = fopen("/dev/urandom", "rb");
+    if (!f) return false;
+    const bool ok = fread(p, 1, n, f) == n;
+    fclose(f);
+    return ok;
+}
+
+// ChaCha20 keystream generator (RFC 8439 block function; 256-bit key, 64-bit stream id, 64-bit block counter).
+// Every purpose draws from its own stream of the context's master key (secret key, public key, relinearization key,
+// one per Galois element, one per encryption), so what a stream yields does not depend on the order in which other
+// streams are consumed, and encryptions can run on several threads.
+struct Rng {
+    uint32_t key[8];
+    u64 stream, block = 0;
+    uint32_t buf[16];
+    int used = 16;
+    Rng(const uint32_t (&k)[8], u64 stream_id) : stream(stream_id) { memcpy(key, k, sizeof key); }
+    static uint32_t rotl32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
+    static void qr(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d)
+    {
+        a += b; d ^= a; d = rotl32(d, 16);
+        c += d; b ^= c; b = rotl32(b, 12);
+        a += b; d ^= a; d = rotl32(d, 8);
+        c += d; b ^= c; b = rotl32(b, 7);
+    }
+    void refill()
+    {
+        uint32_t in[16] = { 0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                            (uint32_t)block, (uint32_t)(block >> 32), (uint32_t)stream, (uint32_t)(stream >> 32) };
+        uint32_t x[16];
+        memcpy(x, in, sizeof x);
+        for (int r = 0; r < 10; r++) {
+            qr(x[0], x[4], x[8], x[12]); qr(x[1], x[5], x[9], x[13]); qr(x[2], x[6], x[10], x[14]); qr(x[3], x[7], x[11], x[15]);
+            qr(x[0], x[5], x[10], x[15]); qr(x[1], x[6], x[11], x[12]); qr(x[2], x[7], x[8], x[13]); qr(x[3], x[4], x[9], x[14]);
+        }
+        for (int i = 0; i < 16; i++) buf[i] = x[i] + in[i];
+        block++;
+        used = 0;
+    }
     u64 next()
     {
-        u64 r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
-        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+        if (used > 14) refill();
+        u64 r = (u64)buf[used] | ((u64)buf[used + 1] << 32);
+        used += 2;
         return r;
     }
     u64 below(u64 q)   // uniform in [0,q) by rejection
@@ -216,6 +258,7 @@ struct Rng {   // xoshiro256**
         for (;;) { u64 v = next(); if (v <= lim) return v % q; }
     }
 };
+enum : u64 { STREAM_SK = 1, STREAM_PK = 2, STREAM_RELIN = 3, STREAM_GALOIS = u64(4) << 32, STREAM_ENCRYPT = u64(5) << 32 };
 }   // namespace
 
 struct hfhe_ctx {
@@ -227,33 +270,34 @@ struct hfhe_ctx {
     u64 t = 0;
     Ntt ntt_t;   // BFV batching
     double scale = 1.0;
-    Rng rng;
+    uint32_t master[8];                        // ChaCha20 key of every stream of this context
+    std::atomic<u64> enc_streams{ 0 };         // encryption streams handed out so far
     std::vector<u64> sk;        // [K][N] NTT form
     std::vector<u64> pk;        // [2][K][N] NTT form
     std::vector<u64> relin;     // [Ltop][2][K][N]
     std::map<uint32_t, std::vector<u64>> galois;
     std::vector<uint32_t> galois_elts, slot_map;   // slot_map: matrix_reps_index_map
     std::vector<std::complex<double>> croots;      // zeta^{bitrev(k)}
-    explicit hfhe_ctx(u64 seed) : rng(seed) {}
 
     void to_rns_signed(const std::vector<int64_t> &v, size_t limbs, u64 *out) const
     {
         for (size_t l = 0; l < limbs; l++)
             for (size_t n = 0; n < N; n++) out[l * N + n] = v[n] >= 0 ? (u64)v[n] % q[l] : q[l] - ((u64)(-v[n]) % q[l]);
     }
-    void sample_ternary(std::vector<int64_t> &v) { for (auto &x : v) x = (int64_t)rng.below(3) - 1; }
-    void sample_error(std::vector<int64_t> &v)
-    {   // centred binomial, 21 coin pairs: sigma ~ 3.24 (SEAL: clipped normal, sigma 3.2)
+    // uniform ternary secret / encryption randomness (SEAL sample_poly_ternary)
+    static void sample_ternary(Rng &rng, std::vector<int64_t> &v) { for (auto &x : v) x = (int64_t)rng.below(3) - 1; }
+    static void sample_error(Rng &rng, std::vector<int64_t> &v)
+    {   // centred binomial, 21 coin pairs: sigma ~ 3.24 (SEAL's default noise since 3.6: sample_poly_cbd, same 21 pairs)
         for (auto &x : v) {
             u64 r = rng.next();
             x = (int64_t)__builtin_popcountll(r & 0x1fffff) - (int64_t)__builtin_popcountll((r >> 21) & 0x1fffff);
         }
     }
     // (b, a) with b = -(a s + e) over `limbs` key-level primes, NTT form; b,a: [limbs][N] strided by K in dst
-    void zero_sym(u64 *b, u64 *a)
+    void zero_sym(Rng &rng, u64 *b, u64 *a)
     {
         std::vector<int64_t> e(N);
-        sample_error(e);
+        sample_error(rng, e);
         std::vector<u64> er(K * N);
         to_rns_signed(e, K, er.data());
         for (size_t l = 0; l < K; l++) {
@@ -267,12 +311,12 @@ struct hfhe_ctx {
         }
     }
     // SEAL KeyGenerator::generate_one_kswitch_key restated: new_key [K][N] NTT form
-    void make_kswitch(const u64 *new_key, std::vector<u64> &out)
+    void make_kswitch(Rng &rng, const u64 *new_key, std::vector<u64> &out)
     {
         out.assign(Ltop * 2 * K * N, 0);
         for (size_t j = 0; j < Ltop; j++) {
             u64 *b = out.data() + (j * 2 + 0) * K * N, *a = out.data() + (j * 2 + 1) * K * N;
-            zero_sym(b, a);
+            zero_sym(rng, b, a);
             u64 factor = q[K - 1] % q[j];
             for (size_t n = 0; n < N; n++) b[j * N + n] = addm(b[j * N + n], mulm(new_key[j * N + n], factor, q[j]), q[j]);
         }
@@ -314,7 +358,19 @@ struct hfhe_ctx {
 
 extern "C" hfhe_ctx *hfhe_create(int scheme, size_t N, size_t depth, int coeff_bits, int sp_bits, uint64_t seed)
 {
-    hfhe_ctx *c = new hfhe_ctx(seed);
+    hfhe_ctx *c = new hfhe_ctx;
+    if (seed == 0) {   // the default: 256 bits from the operating system
+        if (!os_entropy(c->master, sizeof c->master)) { delete c; return nullptr; }
+    } else {           // reproducible runs (tests, bench.py, HEB_B200_SEED): the key is expanded from the seed.  NOT for real keys.
+        for (int i = 0; i < 8; i += 2) {   // splitmix64
+            u64 z = (seed += 0x9e3779b97f4a7c15ull);
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            z ^= z >> 31;
+            c->master[i] = (uint32_t)z;
+            c->master[i + 1] = (uint32_t)(z >> 32);
+        }
+    }
     c->scheme = scheme;
     c->N = N;
     c->K = depth + 1;
@@ -358,16 +414,25 @@ extern "C" hfhe_ctx *hfhe_create(int scheme, size_t N, size_t depth, int coeff_b
     }
     // secret key, public key, relin key
     std::vector<int64_t> s(N);
-    c->sample_ternary(s);
+    {
+        Rng r(c->master, STREAM_SK);
+        hfhe_ctx::sample_ternary(r, s);
+    }
     c->sk.resize(c->K * N);
     c->to_rns_signed(s, c->K, c->sk.data());
     for (size_t l = 0; l < c->K; l++) c->ntt[l].fwd(c->sk.data() + l * N);
     c->pk.resize(2 * c->K * N);
-    c->zero_sym(c->pk.data(), c->pk.data() + c->K * N);
+    {
+        Rng r(c->master, STREAM_PK);
+        c->zero_sym(r, c->pk.data(), c->pk.data() + c->K * N);
+    }
     std::vector<u64> s2(c->K * N);
     for (size_t l = 0; l < c->K; l++)
         for (size_t n = 0; n < N; n++) s2[l * N + n] = mulm(c->sk[l * N + n], c->sk[l * N + n], c->q[l]);
-    c->make_kswitch(s2.data(), c->relin);
+    {
+        Rng r(c->master, STREAM_RELIN);
+        c->make_kswitch(r, s2.data(), c->relin);
+    }
     // default Galois elements: 3^(2^k), 3^-(2^k), then 2N-1
     {
         u64 m = 2 * N, pos = 3, neg = 1;
@@ -404,7 +469,8 @@ extern "C" const uint64_t *hfhe_galois_key(hfhe_ctx *c, uint32_t elt)
     for (size_t l = 0; l < c->K; l++)
         for (size_t n = 0; n < c->N; n++) rs[l * c->N + n] = c->sk[l * c->N + tab[n]];
     std::vector<u64> &dst = c->galois[elt];
-    c->make_kswitch(rs.data(), dst);
+    Rng r(c->master, STREAM_GALOIS | elt);
+    c->make_kswitch(r, rs.data(), dst);
     return dst.data();
 }
 
@@ -483,16 +549,19 @@ extern "C" void hfhe_bfv_decode(hfhe_ctx *c, const uint64_t *plain, int64_t *out
     }
 }
 
-extern "C" void hfhe_encrypt(hfhe_ctx *c, const uint64_t *plain, uint64_t *ct)
+extern "C" uint64_t hfhe_reserve_encryptions(hfhe_ctx *c, uint64_t n) { return c->enc_streams.fetch_add(n); }
+extern "C" void hfhe_encrypt(hfhe_ctx *c, const uint64_t *plain, uint64_t *ct) { hfhe_encrypt_at(c, plain, ct, hfhe_reserve_encryptions(c, 1)); }
+extern "C" void hfhe_encrypt_at(hfhe_ctx *c, const uint64_t *plain, uint64_t *ct, uint64_t index)
 {
     const size_t N = c->N, L = c->Ltop, K = c->K;
+    Rng rng(c->master, STREAM_ENCRYPT + index);
     std::vector<int64_t> u(N), e(N);
-    c->sample_ternary(u);
+    hfhe_ctx::sample_ternary(rng, u);
     std::vector<u64> ur(L * N), er(L * N);
     c->to_rns_signed(u, L, ur.data());
     for (size_t l = 0; l < L; l++) c->ntt[l].fwd(ur.data() + l * N);
     for (size_t k = 0; k < 2; k++) {
-        c->sample_error(e);
+        hfhe_ctx::sample_error(rng, e);
         c->to_rns_signed(e, L, er.data());
         for (size_t l = 0; l < L; l++) {
             c->ntt[l].fwd(er.data() + l * N);

@@ -10,9 +10,13 @@
  * key-switch-key memory layout (uint64[size][L][N], uint64[L_top][2][K][N]), same slot
  * ordering (generator 3 index map) so that Galois element 3^k rotates slots left by k.
  * It is NOT the ciphertext-evaluation path: no Evaluator operation lives here.
- * Randomness is a seeded xoshiro256** (SEAL's is Blake2-XOF seeded from the OS; the
- * reference never fixes it, R/src/engine/seal_context.cpp:87-90), so bit-equality with
- * SEAL's *encryptions* is neither possible nor required.
+ * Randomness: a ChaCha20 keystream keyed with 256 bits from the operating system (seed 0, the
+ * default; SEAL's is a Blake2/Shake XOF seeded from the OS and the reference never fixes it,
+ * R/src/engine/seal_context.cpp:87-90), so bit-equality with SEAL's *encryptions* is neither
+ * possible nor required.  A non-zero seed makes keys and encryptions reproducible: that is for
+ * tests and benchmarks only.  Secret: uniform ternary; noise: centred binomial (21 coin pairs),
+ * SEAL's defaults.  This module is a BENCHMARK STAND-IN for host SEAL, not a vetted cryptographic
+ * library: production deployments bind the real SEAL objects here.
  */
 #ifndef HOSTFHE_H
 #define HOSTFHE_H
@@ -26,7 +30,9 @@ typedef struct hfhe_ctx hfhe_ctx;
 enum { HFHE_BFV = 1, HFHE_CKKS = 2 };
 
 /* coeff_modulus = {60, bits x (depth-1), 60}  (R/src/engine/seal_context.cpp:79-82,107-110);
- * scale_or_plain_bits: CKKS scale exponent, or BFV plain-modulus bits (PlainModulus::Batching). */
+ * scale_or_plain_bits: CKKS scale exponent, or BFV plain-modulus bits (PlainModulus::Batching).
+ * seed: 0 = key material from OS entropy (getrandom); non-zero = reproducible (tests / benchmarks only).
+ * Returns NULL for unsupported parameters or when no entropy source is available. */
 hfhe_ctx *hfhe_create(int scheme, size_t N, size_t depth, int coeff_bits, int scale_or_plain_bits, uint64_t seed);
 void hfhe_destroy(hfhe_ctx *c);
 size_t hfhe_N(const hfhe_ctx *c);
@@ -52,8 +58,13 @@ void hfhe_ckks_decode(hfhe_ctx *c, const uint64_t *plain, size_t L, double scale
 void hfhe_bfv_encode(hfhe_ctx *c, const int64_t *vals, size_t n, uint64_t *plain);
 void hfhe_bfv_decode(hfhe_ctx *c, const uint64_t *plain, int64_t *out /*N*/);
 
-/* public-key encryption at the top data level: ct [2][L_top][N] (CKKS: NTT form; BFV: coeff form) */
+/* public-key encryption at the top data level: ct [2][L_top][N] (CKKS: NTT form; BFV: coeff form).
+ * Thread safe: every encryption draws from its own keystream.  hfhe_encrypt takes the next free stream;
+ * hfhe_reserve_encryptions(n) hands out n consecutive stream indices (returns the first) for callers that
+ * encrypt a vector on several threads with hfhe_encrypt_at and still want reproducible bits under a fixed seed. */
 void hfhe_encrypt(hfhe_ctx *c, const uint64_t *plain, uint64_t *ct);
+uint64_t hfhe_reserve_encryptions(hfhe_ctx *c, uint64_t n);
+void hfhe_encrypt_at(hfhe_ctx *c, const uint64_t *plain, uint64_t *ct, uint64_t index);
 /* decrypt a size-`size` ciphertext at level L: CKKS -> plain [L][N] NTT form; BFV -> plain [N] mod t */
 void hfhe_decrypt(hfhe_ctx *c, const uint64_t *ct, size_t size, size_t L, uint64_t *plain);
 

@@ -66,6 +66,15 @@ def oracle():
         o.orc_batch_dot.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, u64p, C.c_size_t, u64p, u32p,
                                     C.POINTER(u64p), C.c_size_t, u64p, C.c_int]
         o.orc_batch_ntt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, C.c_int, C.c_int]
+        o.orc_selftest_fastmod.restype = C.c_size_t
+        o.orc_selftest_fastmod.argtypes = [C.c_uint64, C.c_size_t, C.c_uint64]
+        kargs = [u64p, u32p, C.POINTER(u64p), C.c_size_t]   # relin, elts, galois keys, count
+        o.orc_matmul_val.argtypes = [C.c_void_p] + [C.c_size_t] * 4 + [u64p, u64p] + kargs + [u64p, C.c_int]
+        o.orc_matmul_row.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, u64p, u64p] + kargs + [u64p, C.c_int]
+        o.orc_matmul_cba.argtypes = [C.c_void_p] + [C.c_size_t] * 4 + [u64p, u64p, u64p, u64p, C.c_int]
+        o.orc_collapse.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, C.c_size_t, u64p, u64p] + kargs[1:] + [u64p, C.c_int]
+        o.orc_horner.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u64p, u64p, u64p]
+        o.orc_logreg.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, u64p, u64p, u64p, u64p, u64p, u64p, C.c_size_t, u64p] + kargs + [u64p, C.c_int]
         _oracle = o
     return _oracle
 
@@ -178,6 +187,57 @@ class Oracle:
                                   len(keys), p64(out), threads)
         assert rc == 0, rc
         return out
+
+
+    # ---- workload bodies (oracle/he_oracle_workloads.cpp): arrays are flat uint64, ciphertexts [count][size][L][N]
+    def matmul_val(self, L, r0, c0, c1, m0, m1t, relin, keys, threads=0):
+        Lout = L - 1 if self.scheme == CKKS else L
+        out = np.empty(r0 * c1 * 2 * Lout * self.N, dtype=np.uint64)
+        elts, arr = self._keyargs(keys)
+        rc = self.o.orc_matmul_val(self.c, L, r0, c0, c1, p64(m0), p64(m1t), p64(relin), elts.ctypes.data_as(u32p), arr, len(keys), p64(out), threads)
+        assert rc == 0, rc
+        return out
+
+    def matmul_row(self, L, nA, dim2, spacers, A, B, relin, keys, threads=0):
+        out = np.empty(nA * 2 * L * self.N, dtype=np.uint64)
+        elts, arr = self._keyargs(keys)
+        rc = self.o.orc_matmul_row(self.c, L, nA, dim2, spacers, p64(A), p64(B), p64(relin), elts.ctypes.data_as(u32p), arr, len(keys), p64(out), threads)
+        assert rc == 0, rc
+        return out
+
+    def matmul_cba(self, L, r0, c0, c1, m0, m1, relin, threads=0):
+        Lout = L - 1 if self.scheme == CKKS else L
+        out = np.empty(r0 * c1 * 2 * Lout * self.N, dtype=np.uint64)
+        rc = self.o.orc_matmul_cba(self.c, L, r0, c0, c1, p64(m0), p64(m1), p64(relin), p64(out), threads)
+        assert rc == 0, rc
+        return out
+
+    def collapse(self, L, n, cts, first_index, masks, zero_ct, keys, threads=0):
+        out = np.empty(2 * (L - 1) * self.N, dtype=np.uint64)
+        elts, arr = self._keyargs(keys)
+        rc = self.o.orc_collapse(self.c, L, n, p64(cts), first_index, p64(masks), p64(zero_ct) if zero_ct is not None else None,
+                                 elts.ctypes.data_as(u32p), arr, len(keys), p64(out), threads)
+        assert rc == 0, rc
+        return out
+
+    def horner(self, Lx, x, seed, coeffs, relin):
+        """coeffs: [ncoef][Ltop][N] flat = the plaintexts of a_{d-1} .. a_0; returns (ciphertext, level)"""
+        Ltop = self.K - 1
+        ncoef = coeffs.size // (Ltop * self.N)
+        out = np.empty(2 * Ltop * self.N, dtype=np.uint64)
+        lv = self.o.orc_horner(self.c, Lx, p64(x), p64(seed), ncoef, p64(coeffs), p64(relin), p64(out))
+        assert lv > 0, lv
+        return out[: 2 * lv * self.N].copy(), lv
+
+    def logreg(self, n_features, batch, W, b, X, masks, zero_ct, seed, coeffs, relin, keys, threads=0):
+        Ltop = self.K - 1
+        ncoef = coeffs.size // (Ltop * self.N)
+        out = np.empty(2 * Ltop * self.N, dtype=np.uint64)
+        elts, arr = self._keyargs(keys)
+        lv = self.o.orc_logreg(self.c, n_features, batch, p64(W), p64(b), p64(X), p64(masks), p64(zero_ct), p64(seed), ncoef, p64(coeffs),
+                               p64(relin), elts.ctypes.data_as(u32p), arr, len(keys), p64(out), threads)
+        assert lv > 0, lv
+        return out[: 2 * lv * self.N].copy(), lv
 
 
 def rand_residues(rng, moduli, shape_prefix, N):
