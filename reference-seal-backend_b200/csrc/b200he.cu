@@ -20,31 +20,9 @@
 #include <vector>
 
 #include "hostmath.h"
-#include "kernels.cuh"
+#include "launch.h"
+#include "kernels_ew.cuh"
 #include "behz.cuh"
-
-#ifndef B200HE_EMU
-#define B200HE_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-// launch with `cluster` consecutive CTAs per thread-block cluster (a limb split over 2^c CTAs, kernels.cuh)
-template <class... KArgs, class... Args>
-static inline void launch_cluster(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, unsigned cluster, Args... args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = cluster > 1 ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through cudaGetLastError() at the call site
-}
-#define B200HE_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) launch_cluster(kernel, (grid), (block), (smem), (stream), (cluster), __VA_ARGS__)
-#endif
 
 using namespace b200he;
 
@@ -188,34 +166,16 @@ static inline void prof_post(b200he_ctx *c)
         B200HE_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);     \
         prof_post(ctx);                                                           \
     } while (0)
-// NTT-bearing kernels: one cluster of 2^c CTAs per limb
-#define LAUNCHC(ctx, cls, kernel, grid, block, smem, ...)                                                        \
-    do {                                                                                                         \
-        prof_pre(ctx, cls);                                                                                      \
-        B200HE_LAUNCH_CLUSTER(kernel, grid, block, smem, (ctx)->stream, 1u << (ctx)->c, __VA_ARGS__);            \
-        prof_post(ctx);                                                                                          \
-    } while (0)
 #define LAUNCH_CHECK() CK(cudaGetLastError())
-
-// dispatch on the CTA-local transform size
-#define NTT_DISPATCH(ctx, STMT)                                   \
-    switch ((ctx)->lognl) {                                       \
-    case 10: { constexpr int LG = 10; STMT; } break;              \
-    case 11: { constexpr int LG = 11; STMT; } break;              \
-    case 12: { constexpr int LG = 12; STMT; } break;              \
-    default: { constexpr int LG = 13; STMT; } break;              \
-    }
-// dispatch on the CTA-local transform size LG and the cluster exponent CC (limbs larger than 8192 coefficients are
-// split over 2 or 4 CTAs of 8192: CC > 0 only with LG = 13)
-#define KERNEL_DISPATCH(ctx, STMT)                                                      \
-    switch ((ctx)->lognl * 4 + (ctx)->c) {                                              \
-    case 40: { constexpr int LG = 10, CC = 0; STMT; } break;                            \
-    case 44: { constexpr int LG = 11, CC = 0; STMT; } break;                            \
-    case 48: { constexpr int LG = 12, CC = 0; STMT; } break;                            \
-    case 52: { constexpr int LG = 13, CC = 0; STMT; } break;                            \
-    case 53: { constexpr int LG = 13, CC = 1; STMT; } break;                            \
-    default: { constexpr int LG = 13, CC = 2; STMT; } break;                            \
-    }
+// the NTT-bearing kernel families live in their own translation units (launch.h); PROF wraps a launcher call with the
+// per-class launch counter / event pair
+#define PROF(ctx, cls, CALL) \
+    do {                     \
+        prof_pre(ctx, cls);  \
+        CALL;                \
+        prof_post(ctx);      \
+    } while (0)
+static inline Geo geo(const b200he_ctx *c) { return Geo{ c->lognl, c->c, c->stream }; }
 
 static inline unsigned blocks_for(size_t threads, unsigned block = 256) { return (unsigned)((threads + block - 1) / block); }
 
@@ -304,7 +264,7 @@ static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std
     for (size_t i = 0; i < M; i++) {
         const u64 q = moduli[i];
         c->mods[i] = make_mod(q, N);
-        NTT_DISPATCH(c, lazy_schedule<LG>(c->mods[i], c->c, (int)c->K));
+        NTT_DISPATCH(*c, lazy_schedule<LG>(c->mods[i], c->c, (int)c->K));
         const u64 ipsi = hm::invmod(psi[i], q);
         u64 p = 1, ip = 1, ipsi_half = 0;
         for (size_t k = 0; k < N; k++) {
@@ -349,20 +309,12 @@ static int build_tables(b200he_ctx *c, const std::vector<u64> &moduli, const std
     return 0;
 }
 
-template <int LG, int CC> static int set_smem_attrs()
+static int set_smem_attrs(const b200he_ctx *c)
 {
-#ifndef B200HE_EMU
-    const int bytes = NttCfg<LG>::SMEM_BYTES;
-    CK(cudaFuncSetAttribute(k_ntt_fwd<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    if (CC == 0) CK(cudaFuncSetAttribute(k_ntt_fwd_p<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, NttFwdPCfg<LG>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute((k_ntt_inv<LG, CC, KIND_BOTH>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute((k_ntt_inv<LG, CC, KIND_INT>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute((k_ntt_inv<LG, CC, KIND_DP>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_moddown_dp<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_moddown_mix<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES));
-#endif
+    const Geo g = geo(c);
+    CK((cudaError_t)smem_attrs_ntt(g));
+    CK((cudaError_t)smem_attrs_ks(g));
+    CK((cudaError_t)smem_attrs_moddown(g));
     return 0;
 }
 
@@ -421,9 +373,7 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("ctx_create: stream"); }
     c->own_stream = true;
 #endif
-    int rc = 0;
-    KERNEL_DISPATCH(c, (rc = set_smem_attrs<LG, CC>()));
-    if (rc) { delete c; return rc; }
+    if (int rc = set_smem_attrs(c)) { delete c; return rc; }
     // pinned staging for load()/store() (page-locking 64 MB takes tens of milliseconds: not inside the first load)
     if (stage_init(c, 0)) { delete c; return -1; }
     // the tables were uploaded with synchronous copies from pageable memory (NULL stream): make sure they have landed
@@ -787,27 +737,16 @@ static void launch_moddown(b200he_ctx *c, ModDownArgs D, size_t polys)
     const unsigned all = D.nJ >= 32 ? ~0u : ((1u << D.nJ) - 1);
     D.jmask = all;
     D.nJsub = D.nJ;
-    const unsigned grid = (unsigned)((polys * D.nJ) << c->c);
-    if (dpmask == 0) {
-        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, c->T, D));
-    } else if (dpmask == all) {
-        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown_dp<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, c->T, D));
-    } else {
-        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_MODDOWN, (k_moddown_mix<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, c->T, D));
-    }
+    const int kind = dpmask == 0 ? KIND_INT : dpmask == all ? KIND_DP : KIND_BOTH;
+    PROF(c, B200HE_KERN_MODDOWN, launch_moddown_kind(geo(c), kind, c->T, D, polys * D.nJ));
 }
 static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base)
 {
     if (!nlimbs) return 0;
     static const bool persistent = !(getenv("B200HE_NO_PERSISTENT") && atoi(getenv("B200HE_NO_PERSISTENT")));
-    if (c->c == 0 && persistent && nlimbs > (size_t)c->n_sm) {   // unsplit limbs, more than one wave: persistent CTAs with TMA prefetch
-        NTT_DISPATCH(c, LAUNCH(c, B200HE_KERN_NTT_FWD, k_ntt_fwd_p<LG>, (unsigned)c->n_sm, NttCfg<LG>::THREADS, NttFwdPCfg<LG>::SMEM_BYTES, c->T, src, dst,
-                               src_outer, dst_outer, L, mod_base, (int)nlimbs));
-        LAUNCH_CHECK();
-        return 0;
-    }
-    KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_FWD, (k_ntt_fwd<LG, CC>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                               c->T, src, dst, src_outer, dst_outer, L, mod_base));
+    // unsplit limbs, more than one wave: persistent CTAs with TMA prefetch
+    const unsigned pctas = (c->c == 0 && persistent && nlimbs > (size_t)c->n_sm) ? (unsigned)c->n_sm : 0u;
+    PROF(c, B200HE_KERN_NTT_FWD, launch_ntt_fwd(geo(c), c->T, src, dst, src_outer, dst_outer, L, mod_base, nlimbs, pctas));
     LAUNCH_CHECK();
     return 0;
 }
@@ -820,16 +759,8 @@ static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_
     // kinds of moduli among the launch's limbs (modulus ids mod_base .. mod_base + L - 1)
     int n_dp = 0;
     for (int l = 0; l < L; l++) n_dp += c->mods[mod_base + l].dp ? 1 : 0;
-    if (n_dp == 0) {
-        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC, KIND_INT>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                                   c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
-    } else if (n_dp == L) {
-        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC, KIND_DP>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                                   c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
-    } else {
-        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_NTT_INV, (k_ntt_inv<LG, CC, KIND_BOTH>), (unsigned)(nlimbs << c->c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES,
-                                   c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
-    }
+    const int kind = n_dp == 0 ? KIND_INT : n_dp == L ? KIND_DP : KIND_BOTH;
+    PROF(c, B200HE_KERN_NTT_INV, launch_ntt_inv(geo(c), kind, c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F, nlimbs));
     LAUNCH_CHECK();
     return 0;
 }
@@ -1061,8 +992,7 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
         }
         A.key = key; A.acc = acc; A.rp = rp; A.L = L; A.K = (int)K; A.B = (int)nb;
         // (the rounded special-prime limb comes out of k_ks_inner in coefficient form: rp)
-        KERNEL_DISPATCH(c, LAUNCHC(c, B200HE_KERN_KS_INNER, (k_ks_inner<LG, CC>), (unsigned)((nb * (L + 1)) << c->c), NttCfg<LG>::THREADS,
-                                   KsCfg<LG>::SMEM_BYTES, c->T, A));
+        PROF(c, B200HE_KERN_KS_INNER, launch_ks_inner(geo(c), c->T, A, nb * (L + 1)));
         if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: k_ks_inner launch failed"); break; }
         ModDownArgs D{};
         D.rp = rp; D.base = acc; D.base_ct_stride = w_acc; D.base_poly_stride = (size_t)(L + 1) * N;

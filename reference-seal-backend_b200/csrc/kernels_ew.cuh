@@ -1,0 +1,217 @@
+// kernels_ew.cuh -- the non-template kernels of the hot path: elementwise / tensor / Galois / copy kernels, the key
+// upload transform and the coefficient-form mod-down.  Included by exactly ONE translation unit (b200he.cu): plain
+// __global__ functions have external linkage.  The NTT-bearing template kernels live in kernels.cuh and are instantiated
+// in their own translation units (tu_ntt.cu, tu_ks.cu, tu_moddown.cu) so that the kernel families compile in parallel.
+#pragma once
+#include "kernels.cuh"
+
+namespace b200he {
+
+__global__ void __launch_bounds__(256) k_shoup_quotients(Tables T, const u64 *__restrict__ key, u64 *__restrict__ dkey, int K, size_t words, int lognl)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= words) return;
+    const Mod &m = T.mods[(gid / T.N) % K];
+    const u64 q = m.q;
+    const size_t o = key_word_index(gid / T.N, gid % T.N, T.N, lognl);
+    u64 rem = key[gid], quot = 0;
+    if (m.dp) {   // FP64-domain modulus: the residue as a double, [p][tid][2] in the first half of the limb's slot
+        const size_t e = gid % T.N, NL = (size_t)1 << lognl, TH = NL / 16, el = e & (NL - 1);
+        dkey[2 * ((gid / T.N) * T.N + (e >> lognl) * NL) + (((el & 15) >> 1) * TH + (el >> 4)) * 2 + (el & 1)] = as_u(dp_from(rem));
+        return;
+    }
+    dkey[o] = rem;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        rem <<= 1;
+        quot <<= 1;
+        if (rem >= q) {
+            rem -= q;
+            quot |= 1;
+        }
+    }
+    dkey[o + 2] = quot;
+}
+
+// Coefficient-form variant (BFV key switch / BFV mod-switch): no transform, one thread per coefficient pair.
+// base must already be in coefficient form.  grid covers B * P * nJ * N / 2 threads.
+__global__ void __launch_bounds__(256) k_moddown_coeff(Tables T, ModDownArgs A, size_t B)
+{
+    const size_t N = T.N, per_ct = (size_t)A.P * A.nJ * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * per_ct) return;
+    const size_t b = gid / per_ct, rem = (gid % per_ct) * 2;
+    const size_t limb = rem / N, e = rem % N;
+    const int p = (int)(limb / A.nJ), j = (int)(limb % A.nJ);
+    const Mod m = T.mods[j];
+    const u64 fix = m.q - T.halfmod[(size_t)A.x * T.M + j];
+    const ulonglong2 qi = T.qinv[(size_t)A.x * T.M + j];
+    ulonglong2 r;
+    if (A.rp) r = ld2(A.rp + (b * A.P + p) * N + e);
+    else {
+        const Mod mx = T.mods[A.x];
+        r = ld2(A.rp_raw + (b * A.P + p) * A.rp_raw_stride + e);
+        r.x = csub(r.x + (mx.q >> 1), mx.q);
+        r.y = csub(r.y + (mx.q >> 1), mx.q);
+    }
+    const u64 u0 = csub(reduce64(r.x, m) + fix, m.q), u1 = csub(reduce64(r.y, m) + fix, m.q);
+    const ulonglong2 bv = ld2(A.base + b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + e);
+    u64 v0 = shoup(sub_mod(bv.x, u0, m.q), qi.x, qi.y, m.q);
+    u64 v1 = shoup(sub_mod(bv.y, u1, m.q), qi.x, qi.y, m.q);
+    if (A.addend[p]) {
+        const ulonglong2 av = ld2(A.addend[p] + b * A.add_ct_stride + (size_t)j * N + e);
+        v0 = add_mod(v0, av.x, m.q);
+        v1 = add_mod(v1, av.y, m.q);
+    }
+    st2(A.out + b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + e, v0, v1);
+}
+
+// ------------------------------------------------------------------------------------ K3 / K4 / K11
+// Elementwise kernels: one thread per coefficient pair; ciphertext i of the output pairs
+// a[ai[i]] with b[bi[i]] (index maps express the reference's b0 x b1 result grid without copies).
+enum { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2 };
+struct EwArgs {
+    const u64 *a, *b;
+    u64 *out;
+    const u32 *ai, *bi;         // nullable
+    size_t a_stride, b_stride, out_stride;   // words per ciphertext
+    int polys, b_polys;         // polys in out/a; polys in b (1 = plaintext broadcast over polys / only c0 for add)
+    int L, mod_base;
+    size_t n;                   // ciphertexts
+};
+template <int OP> __global__ void __launch_bounds__(256) k_ew(Tables T, EwArgs A)
+{
+    const size_t N = T.N, per_ct = (size_t)A.polys * A.L * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n * per_ct) return;
+    const size_t i = gid / per_ct, rem = (gid % per_ct) * 2;
+    const size_t limb_idx = rem / N, e = rem % N;
+    const int p = (int)(limb_idx / A.L), l = (int)(limb_idx % A.L);
+    const Mod m = T.mods[A.mod_base + l];
+    const size_t ia = A.ai ? A.ai[i] : i, ib = A.bi ? A.bi[i] : i;
+    ulonglong2 va = ld2(A.a + ia * A.a_stride + rem);
+    u64 *o = A.out + i * A.out_stride + rem;
+    if (A.b_polys == 1 && p > 0 && OP != EW_MUL) {   // add_plain / sub_plain touch c0 only
+        st2(o, va.x, va.y);
+        return;
+    }
+    const size_t boff = (A.b_polys == 1 ? 0 : (size_t)p * A.L * N) + (size_t)l * N + e;
+    ulonglong2 vb = ld2(A.b + ib * A.b_stride + boff);
+    if (OP == EW_ADD) st2(o, add_mod(va.x, vb.x, m.q), add_mod(va.y, vb.y, m.q));
+    else if (OP == EW_SUB) st2(o, sub_mod(va.x, vb.x, m.q), sub_mod(va.y, vb.y, m.q));
+    else if (m.dp)
+        st2(o, dp_canon(dp_mul_dd(dp_from(va.x), dp_from(vb.x), m.dqinv, m.dnq), m), dp_canon(dp_mul_dd(dp_from(va.y), dp_from(vb.y), m.dqinv, m.dnq), m));
+    else st2(o, mul_mod(va.x, vb.x, m), mul_mod(va.y, vb.y, m));
+}
+
+// CKKS / NTT-domain tensor product (2 x 2 -> 3): reads 4 polys, writes 3, one pass.
+__global__ void __launch_bounds__(256) k_tensor(Tables T, EwArgs A)
+{
+    const size_t N = T.N, LN = (size_t)A.L * N, per_ct = LN / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n * per_ct) return;
+    const size_t i = gid / per_ct, rem = (gid % per_ct) * 2;
+    const int l = (int)(rem / N);
+    const Mod m = T.mods[A.mod_base + l];
+    const size_t ia = A.ai ? A.ai[i] : i, ib = A.bi ? A.bi[i] : i;
+    const u64 *pa = A.a + ia * A.a_stride + rem, *pb = A.b + ib * A.b_stride + rem;
+    ulonglong2 a0 = ld2(pa), a1 = ld2(pa + LN), b0 = ld2(pb), b1 = ld2(pb + LN);
+    u64 *o = A.out + i * A.out_stride + rem;
+    if (m.dp) {   // FP64 domain (warp-uniform: a warp's coefficient pairs belong to one limb): 4 exact products per coefficient
+        const double qi = m.dqinv, nq = m.dnq;
+        const double x0 = dp_from(a0.x), x1 = dp_from(a1.x), y0 = dp_from(b0.x), y1 = dp_from(b1.x);
+        const double u0 = dp_from(a0.y), u1 = dp_from(a1.y), v0 = dp_from(b0.y), v1 = dp_from(b1.y);
+        st2(o, dp_canon(dp_mul_dd(x0, y0, qi, nq), m), dp_canon(dp_mul_dd(u0, v0, qi, nq), m));
+        st2(o + LN, dp_canon(__dadd_rn(dp_mul_dd(x0, y1, qi, nq), dp_mul_dd(x1, y0, qi, nq)), m),
+            dp_canon(__dadd_rn(dp_mul_dd(u0, v1, qi, nq), dp_mul_dd(u1, v0, qi, nq)), m));
+        st2(o + 2 * LN, dp_canon(dp_mul_dd(x1, y1, qi, nq), m), dp_canon(dp_mul_dd(u1, v1, qi, nq), m));
+        return;
+    }
+    st2(o, mul_mod(a0.x, b0.x, m), mul_mod(a0.y, b0.y, m));
+    st2(o + LN, mad_mod(a0.x, b1.x, mul_mod(a1.x, b0.x, m), m), mad_mod(a0.y, b1.y, mul_mod(a1.y, b0.y, m), m));
+    st2(o + 2 * LN, mul_mod(a1.x, b1.x, m), mul_mod(a1.y, b1.y, m));
+}
+
+// ------------------------------------------------------------------------------------ K8
+// NTT-form Galois automorphism of a size-2 ciphertext batch: out0 = g(c0) -> dst ct poly 0,
+// g(c1) -> target buffer [B][L][N]; dst poly 1 is produced by the key switch that follows.
+struct GaloisArgs {
+    const u64 *src;       // [B][2][L][N]
+    u64 *dst0;            // g(c0): dst0 + b*dst_stride + l*N
+    u64 *dst1;            // g(c1): dst1 + b*L*N + l*N
+    size_t src_stride, dst_stride;
+    const u32 *table;     // [N] NTT-form permutation (CKKS)
+    u32 elt;              // Galois element (BFV coefficient form)
+    int L, logn;
+    size_t B;
+    int add_input;        // dst0 = g(c0) + c0 (rotate-and-add of accumulate: the key switch then adds c1 as its second addend)
+};
+__global__ void __launch_bounds__(256) k_galois_ntt(Tables T, GaloisArgs A)
+{
+    const size_t N = T.N, per_ct = 2 * (size_t)A.L * N;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.B * per_ct) return;
+    const size_t b = gid / per_ct, rem = gid % per_ct;
+    const size_t p = rem / ((size_t)A.L * N), le = rem % ((size_t)A.L * N), l = le / N, e = le % N;
+    const u64 v = A.src[b * A.src_stride + p * A.L * N + l * N + A.table[e]];
+    if (p == 0) A.dst0[b * A.dst_stride + le] = A.add_input ? add_mod(v, A.src[b * A.src_stride + le], T.mods[l].q) : v;
+    else A.dst1[b * A.L * N + le] = v;
+}
+// Coefficient-form automorphism (BFV): coefficient i moves to i*elt mod N, negated when floor(i*elt/N) is odd.
+__global__ void __launch_bounds__(256) k_galois_coeff(Tables T, GaloisArgs A)
+{
+    const size_t N = T.N, per_ct = 2 * (size_t)A.L * N;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.B * per_ct) return;
+    const size_t b = gid / per_ct, rem = gid % per_ct;
+    const size_t p = rem / ((size_t)A.L * N), le = rem % ((size_t)A.L * N), l = le / N, i = le % N;
+    const u64 q = T.mods[l].q;
+    u64 v = A.src[b * A.src_stride + rem];
+    const u64 raw = (u64)i * A.elt;
+    const size_t idx = raw & (N - 1);
+    if ((raw >> A.logn) & 1) v = v ? q - v : 0;
+    if (p == 0) A.dst0[b * A.dst_stride + l * N + idx] = A.add_input ? add_mod(v, A.src[b * A.src_stride + l * N + idx], q) : v;
+    else A.dst1[b * A.L * N + l * N + idx] = v;
+}
+
+// strided copy of polys/limbs (mod_switch_drop_to_next, ciphertext gather): out[i][p][l] = in[idx[i]][p][l], l < L_out
+struct CopyArgs {
+    const u64 *src;
+    u64 *dst;
+    const u32 *idx;       // gather map (source ciphertext of output i), nullable
+    const u32 *dst_idx;   // scatter map (destination ciphertext of item i), nullable
+    size_t src_stride, dst_stride;
+    int polys, L_in, L_out;
+    size_t n;
+};
+__global__ void __launch_bounds__(256) k_copy_limbs(Tables T, CopyArgs A)
+{
+    const size_t N = T.N, per_ct = (size_t)A.polys * A.L_out * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n * per_ct) return;
+    const size_t i = gid / per_ct, rem = (gid % per_ct) * 2;
+    const size_t limb_idx = rem / N, e = rem % N, p = limb_idx / A.L_out, l = limb_idx % A.L_out;
+    const size_t is = A.idx ? A.idx[i] : i, id = A.dst_idx ? A.dst_idx[i] : i;
+    ulonglong2 v = ld2(A.src + is * A.src_stride + (p * A.L_in + l) * N + e);
+    st2(A.dst + id * A.dst_stride + rem, v.x, v.y);
+}
+
+// out[0] = sum_i in[i] over a batch (collapse of per-sample ciphertexts, R/src/engine/seal_context.cpp:397-400):
+// one thread per coefficient pair walks the batch; modular adds commute, so any order gives the reference's bits.
+__global__ void __launch_bounds__(256) k_batch_sum(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst, size_t n, int polys, int L)
+{
+    const size_t N = T.N, per_ct = (size_t)polys * L * N / 2;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_ct) return;
+    const size_t rem = gid * 2;
+    const u64 q = T.mods[(rem / N) % L].q;
+    u64 s0 = 0, s1 = 0;
+    for (size_t i = 0; i < n; i++) {
+        const ulonglong2 v = ld2(src + i * 2 * per_ct + rem);
+        s0 = add_mod(s0, v.x, q);
+        s1 = add_mod(s1, v.y, q);
+    }
+    st2(dst + rem, s0, s1);
+}
+
+}   // namespace b200he

@@ -1,0 +1,37 @@
+// tu_moddown.cu -- instantiations and launcher of the NTT-form mod-down kernels k_moddown / k_moddown_dp / k_moddown_mix
+// (K6 step 3, K9).
+#include "launch.h"
+
+namespace b200he {
+
+void launch_moddown_kind(const Geo &g, int kind, const Tables &T, const ModDownArgs &D, size_t units)
+{
+    const unsigned grid = (unsigned)(units << g.c);
+    if (kind == KIND_INT) {
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, D));
+    } else if (kind == KIND_DP) {
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_dp<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, D));
+    } else {
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_mix<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, D));
+    }
+}
+
+template <int LG, int CC> static int attrs()
+{
+#ifndef B200HE_EMU
+    cudaError_t e = cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_moddown_dp<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_moddown_mix<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES);
+    return (int)e;
+#else
+    return 0;
+#endif
+}
+int smem_attrs_moddown(const Geo &g)
+{
+    int rc = 0;
+    KERNEL_DISPATCH(g, (rc = attrs<LG, CC>()));
+    return rc;
+}
+
+}   // namespace b200he

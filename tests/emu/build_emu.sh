@@ -4,6 +4,16 @@
 set -e
 here=$(cd "$(dirname "$0")" && pwd)
 root=$(cd "$here/../.." && pwd)
-g++ -O2 -pthread -ffp-contract=off -std=c++17 -fPIC -shared -DB200HE_EMU -x c++ -I"$root/tests" -I"$root/reference-seal-backend_b200/csrc" \
-    -Wno-unknown-pragmas -o "$here/libb200he_emu.so" \
-    "$root/reference-seal-backend_b200/csrc/b200he.cu" "$here/cuda_shim.cpp"
+csrc="$root/reference-seal-backend_b200/csrc"
+obj="$here/obj"
+mkdir -p "$obj"
+FLAGS="-O2 -pthread -ffp-contract=off -std=c++17 -fPIC -DB200HE_EMU -I$root/tests -I$csrc -Wno-unknown-pragmas"
+pids=""
+for u in b200he tu_ntt tu_ks tu_moddown; do
+    g++ $FLAGS -x c++ -c -o "$obj/$u.o" "$csrc/$u.cu" &
+    pids="$pids $!"
+done
+g++ $FLAGS -c -o "$obj/cuda_shim.o" "$here/cuda_shim.cpp" &
+pids="$pids $!"
+for p in $pids; do wait "$p"; done
+g++ -shared -pthread -o "$here/libb200he_emu.so" "$obj/b200he.o" "$obj/tu_ntt.o" "$obj/tu_ks.o" "$obj/tu_moddown.o" "$obj/cuda_shim.o"

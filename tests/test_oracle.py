@@ -245,3 +245,171 @@ def test_bfv_multiply_and_rotate_decrypt_correctly():
     assert np.array_equal(rot, want)
     down = orc.rescale(L, 2, ct2)   # BFV mod_switch_to_next keeps the plaintext
     assert np.array_equal(host.dec_vec(down, 2, L - 1), x * y)
+
+
+# ------------------------------------------------------------------------------- exact statements: key switch, BEHZ
+N_TINY = 64   # big-integer polynomial arithmetic in pure Python
+
+
+def negacyclic_full(a, b, q):
+    n = len(a)
+    out = [0] * n
+    for i, ai in enumerate(a):
+        for j, bj in enumerate(b):
+            k = i + j
+            if k < n:
+                out[k] += ai * bj
+            else:
+                out[k - n] -= ai * bj
+    return [v % q for v in out]
+
+
+@pytest.mark.parametrize("scheme", [CKKS, BFV], ids=["ckks", "bfv"])
+def test_switch_key_is_rounded_division_by_the_special_prime(scheme):
+    """Evaluator::switch_key_inplace (SURVEY A.8), as one statement over the integers: with d_J the NON-centred digits of
+    the target (coefficient form, 0 <= d_J < q_J), K_{J,k} the key polynomials and P the special prime,
+        A_k   = sum_J d_J (*) K_{J,k}  mod (q_0 ... q_{L-1} P)      (negacyclic products, canonical representative)
+        out_k = c_k + floor((A_k + floor(P/2)) / P)   mod q_j
+    -- a rounding or digit-lift convention that differs by one from this shows up in the low bits, which the decrypt-level
+    tests cannot see."""
+    N = N_TINY
+    moduli = chain(N, [60, 45, 40, 60])
+    q = [int(v) for v in moduli]
+    K, P = len(q), q[-1]
+    t = int(oracle().orc_plain_modulus_batching(N, 20)) if scheme == BFV else 0
+    orc = Oracle(scheme, N, moduli, t)
+    rng = np.random.default_rng(21)
+    key = rand_residues(rng, moduli, (K - 1, 2), N)                      # [Ltop][2][K][N], NTT form
+    key_coeff = [[[[int(v) for v in orc.ntt(i, key[J, k, i], inverse=True)] for i in range(K)] for k in range(2)] for J in range(K - 1)]
+    for L in (K - 1, K - 2):
+        ct = rand_residues(rng, moduli[:L], (2,), N)
+        target = rand_residues(rng, moduli[:L], (), N)
+        got = orc.switch_key(L, ct.reshape(-1), target.reshape(-1), key.reshape(-1)).reshape(2, L, N)
+        if scheme == CKKS:   # ciphertext and target are in NTT form
+            digits = [[int(v) for v in orc.ntt(J, target[J], inverse=True)] for J in range(L)]
+            c_coeff = [[[int(v) for v in orc.ntt(j, ct[k, j], inverse=True)] for j in range(L)] for k in range(2)]
+            got_coeff = [[[int(v) for v in orc.ntt(j, got[k, j], inverse=True)] for j in range(L)] for k in range(2)]
+        else:
+            digits = [[int(v) for v in target[J]] for J in range(L)]
+            c_coeff = [[[int(v) for v in ct[k, j]] for j in range(L)] for k in range(2)]
+            got_coeff = [[[int(v) for v in got[k, j]] for j in range(L)] for k in range(2)]
+        out_mods = q[:L] + [P]
+        for k in range(2):
+            acc = []   # A_k modulo each of q_0..q_{L-1}, P
+            for idx, qi in enumerate(out_mods):
+                ki = idx if idx < L else K - 1
+                s = [0] * N
+                for J in range(L):
+                    prod = negacyclic_full(digits[J], key_coeff[J][k][ki], qi)
+                    s = [(x + y) % qi for x, y in zip(s, prod)]
+                acc.append(s)
+            for n in range(N):
+                A = crt([acc[i][n] for i in range(L + 1)], out_mods)
+                rounded = (A + P // 2) // P
+                for j in range(L):
+                    assert got_coeff[k][j][n] == (c_coeff[k][j][n] + rounded) % q[j], (scheme, L, k, j, n)
+
+
+def is_prime(n):
+    if n < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % p == 0:
+            return n == p
+    d, r = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        r += 1
+    for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(r - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def fastbconv(res, base, p):
+    """Bajard et al. fast base conversion: sum_i [x_i (b/b_i)^-1]_{b_i} (b/b_i) mod p, over the integers"""
+    b = 1
+    for v in base:
+        b *= v
+    tot = 0
+    for x, bi in zip(res, base):
+        punct = b // bi
+        tot += (x * pow(punct, -1, bi) % bi) * punct
+    return tot % p
+
+
+def test_bfv_multiply_is_behz_step_by_step():
+    """Evaluator::bfv_multiply (SURVEY A.12) restated independently with Python integers -- base extension with the small
+    Montgomery reduction, tensor product in q and Bsk, multiplication by t, fast floor, Shenoy-Kumaresan conversion --
+    and compared with the oracle word for word.  (BEHZ is approximate by design: the statement is the algorithm, step by
+    step, not round(t x y / q).)"""
+    N = N_TINY
+    moduli = chain(N, [60, 40, 60])
+    q = [int(v) for v in moduli[:2]]
+    L = len(q)
+    t = int(oracle().orc_plain_modulus_batching(N, 20))
+    orc = Oracle(BFV, N, moduli, t)
+    Q = q[0] * q[1]
+    nB = L + (1 if 32 + t.bit_length() + Q.bit_length() >= 61 * L + 61 else 0)
+    pr, v = [], ((1 << 61) - 1) // (2 * N) * (2 * N) + 1     # descending candidates = 1 mod 2N below 2^61
+    while len(pr) < nB + 2:
+        if is_prime(v):
+            pr.append(v)
+        v -= 2 * N
+    m_sk, B = pr[0], pr[2:]
+    Bsk = B + [m_sk]
+    bsk_orc = np.zeros(orc.o.orc_ctx_bsk_size(orc.c), dtype=np.uint64)
+    orc.o.orc_ctx_bsk(orc.c, p64(bsk_orc))
+    assert [int(x) for x in bsk_orc] == Bsk
+    mt = 1 << 32
+    Bprod = 1
+    for x in B:
+        Bprod *= x
+    rng = np.random.default_rng(22)
+    a = rand_residues(rng, moduli[:L], (2,), N)
+    b = rand_residues(rng, moduli[:L], (2,), N)
+
+    def extend(x):   # x: [L][N] residues -> residues in Bsk after the small Montgomery reduction
+        out = [[0] * N for _ in Bsk]
+        for n in range(N):
+            xt = [int(x[i][n]) * mt % q[i] for i in range(L)]
+            r = (-fastbconv(xt, q, mt) * pow(Q, -1, mt)) % mt
+            if r >= mt // 2:
+                r -= mt
+            for pi, p in enumerate(Bsk):
+                out[pi][n] = (fastbconv(xt, q, p) + Q * r) * pow(mt, -1, p) % p
+        return out
+
+    aq = [[[int(v) for v in a[p][i]] for i in range(L)] for p in range(2)]
+    bq = [[[int(v) for v in b[p][i]] for i in range(L)] for p in range(2)]
+    ab, bb = [extend(a[p]) for p in range(2)], [extend(b[p]) for p in range(2)]
+
+    def tensor(x, y, base):   # 3 polynomials per base prime
+        out = []
+        for i, p in enumerate(base):
+            d0 = negacyclic_full(x[0][i], y[0][i], p)
+            d1 = [(u + w) % p for u, w in zip(negacyclic_full(x[0][i], y[1][i], p), negacyclic_full(x[1][i], y[0][i], p))]
+            d2 = negacyclic_full(x[1][i], y[1][i], p)
+            out.append((d0, d1, d2))
+        return out
+
+    dq, db = tensor(aq, bq, q), tensor(ab, bb, Bsk)
+    got = orc.bfv_multiply(a.reshape(-1), b.reshape(-1)).reshape(3, L, N)
+    for c in range(3):
+        for n in range(N):
+            yq = [t * dq[i][c][n] % q[i] for i in range(L)]
+            z = [(t * db[pi][c][n] - fastbconv(yq, q, p)) * pow(Q, -1, p) % p for pi, p in enumerate(Bsk)]
+            zB = z[:nB]
+            alpha = (fastbconv(zB, B, m_sk) - z[nB]) * pow(Bprod, -1, m_sk) % m_sk
+            if alpha > m_sk // 2:
+                alpha -= m_sk   # centred
+            for i in range(L):
+                want = (fastbconv(zB, B, q[i]) - alpha * Bprod) % q[i]
+                assert int(got[c, i, n]) == want, (c, i, n)
