@@ -1,16 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- HEBench samples/s of the ciphertext-evaluation hot path on B200.
 
-Workload (BASELINE.json configs[1]): CKKS element-wise multiply + relinearize + rescale,
+Headline workload (BASELINE.json configs[1]): CKKS element-wise multiply + relinearize + rescale,
 N = 8192, coefficient modulus {60,45,60} (3 limbs at key level, 2 data limbs), 1000 ciphertext
 pairs per GPU per step.  One "sample" = one result ciphertext.  Inputs are synthetic: uniform random
 residues (seed 1234), real key-switching keys from the host FHE stand-in.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            the B200 arm
     python bench.py --impl reference [...]                          the CPU arm (SEAL-restatement oracle)
+    python bench.py --configs none|all|C1,C3,...                    which BASELINE configs run through the plugin (default all)
 
-N > 1: launched by torchrun, one rank per GPU; the batch is sharded (weak scaling: 1000 pairs per GPU),
-no data-path collective; torch.distributed is used for the barrier and the max-over-ranks time only.
+The JSON line carries, beside the contract's keys:
+  * `configs`: EVERY BASELINE.json config at its stated shape through the HEBench plugin (libhebench_seal_backend.so driven
+    by the mini harness in HEBench order: encode, encrypt, load, operate, store, decrypt, decode with pageable host
+    ciphertexts, decoded results validated): samples/s of operate(), end-to-end samples/s over load + operate + store, the
+    dominant kernel and its two roofline fractions (from the library's own work accounting, b200he_profile_work);
+  * `sustained`: the headline step run back to back for >= 1 s with its clock / power record.
+
+N > 1: launched by torchrun, one rank per GPU; the headline batch is sharded (weak scaling: 1000 pairs per GPU),
+no data-path collective; torch.distributed is used for the barrier and the max-over-ranks time only.  The plugin's
+own multi-GPU path (one process, HEB_B200_GPUS = N) is then driven by rank 0 for the strong-scaling configs (C3's
+10^4-result grid, C5's batch: fixed work split over N GPUs) while the other ranks wait.
 """
 import argparse
 import json
@@ -69,6 +79,7 @@ class ClockSampler:
 
     def __init__(self, gpu, period=0.002):
         self.gpu, self.sm, self.mx, self.reasons, self.stop = gpu, [], None, set(), threading.Event()
+        self.power = []
         self.period = period
         self.t = threading.Thread(target=self.run, daemon=True)
         self.n = 0
@@ -83,6 +94,10 @@ class ClockSampler:
                     "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
             while True:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
@@ -122,7 +137,10 @@ class ClockSampler:
 
     def summary(self):
         sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": self.n}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": self.n}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 def bind_to_gpu_numa_node(gpu):
@@ -162,52 +180,110 @@ def synth_inputs(moduli, n, L, N, seed):
     return out
 
 
-# butterfly-equivalents (one modular multiply each) per launch of each NTT-bearing kernel class, averaged over the
-# launches of that class in one step, split by the pipe that executes them: returns
-# (integer-pipe butterflies, FP64-pipe butterflies).  dp[i] = modulus i of the chain runs in the FP64 domain.
-def butterfly_equivalents(cls, B, L, K, N, dp):
-    bf = (N // 2) * (N.bit_length() - 1)
-    w = [0.0, 0.0]
-    if cls == "k_ks_inner":
-        # output modulus I < L: L-1 forward NTTs (the I == J digit is reused in NTT form) + 2 L N MACs;
-        # special prime: L forward + 2 inverse NTTs + 2 L N MACs
-        for I in range(L):
-            w[dp[I]] += (L - 1) * bf + 2 * L * N
-        w[dp[K - 1]] += (L + 2) * bf + 2 * L * N
-    elif cls == "k_moddown":
-        # fused relinearize+rescale mod-down of the L-1 surviving limbs: 2 NTTs per limb; the 4 Shoup scalings per
-        # coefficient and poly run on the integer pipe in either domain
-        for j in range(L - 1):
-            w[dp[j]] += 2 * bf
-            w[0] += 8 * N
-    elif cls == "k_ntt_inv":
-        # two launches: the relinearization target (one limb per data modulus) and the fused last limb (2 limbs at
-        # modulus L-1 + 2 integer scalings per coefficient); averaged per launch
-        for j in range(L):
-            w[dp[j]] += bf / 2.0
-        w[dp[L - 1]] += 2 * bf / 2.0
-        w[0] += 4 * N / 2.0
-    else:
-        return None
-    return w[0] * B, w[1] * B
+def kernel_rooflines(prof, work, steps, peak_hbm, bf_int_peak, bf_dp_peak):
+    """per kernel class: average launch time, HBM fraction (algorithmic bytes / time / measured copy bandwidth) and
+    arithmetic-pipe fraction (time the launch's butterflies need at the measured register-resident rates of the integer
+    and FP64 pipes / measured time).  prof: {class: (ms, launches)}, work: {class: (bfly_int, bfly_fp64, bytes)} from
+    the library's own accounting (b200he_profile_work), both summed over `steps` steps."""
+    out = {}
+    for name, (ms, n) in prof.items():
+        bi, bd, by = work.get(name, (0.0, 0.0, 0.0))
+        sec = ms / 1e3
+        floor_s = bi / bf_int_peak + bd / bf_dp_peak
+        out[name] = {"ms_per_step": ms / steps, "launches_per_step": n / steps,
+                     "hbm_GBps": by / sec / 1e9 if sec > 0 else None, "hbm_frac": by / sec / 1e9 / peak_hbm if sec > 0 else None,
+                     "pipe_frac": floor_s / sec if sec > 0 and floor_s > 0 else None,
+                     "butterflies_per_s": (bi + bd) / sec if sec > 0 and (bi + bd) > 0 else None,
+                     "fp64_share_of_butterflies": bd / (bi + bd) if (bi + bd) > 0 else None,
+                     "algorithmic_bytes_per_launch": by / n if n else None}
+    return out
 
 
-# per-launch algorithmic bytes of each kernel class for this workload (DESIGN.md "Kernels"), W = 8 B
-def algorithmic_bytes(cls, B, L, K, N, dp):
-    W = 8
-    key_words = sum(1 if dp[i] else 2 for i in list(range(L)) + [K - 1])   # per coefficient, digit and component
-    return {
-        "k_tensor": (4 + 3) * L * N * W * B,
-        # two k_ntt_inv launches per step: relinearization target (L limbs in, L out) and the fused last limb
-        # (accumulator, input ciphertext and rounded special-prime limb in, rounded last limb out; 2 polys)
-        "k_ntt_inv": (2 * L + 8) * N * W * B / 2.0,
-        # reads target in coefficient + NTT form, writes 2L accumulator limbs and the 2 rounded special-prime limbs;
-        # key read once per launch (16 B per coefficient with its Shoup quotient, 8 B for FP64-domain limbs)
-        "k_ks_inner": (2 * L + 2 * (L + 1)) * N * W * B + 2 * L * key_words * N * W,
-        # one launch per step (fused relinearize+rescale): both rounded limbs (2 + 2), then per surviving limb and poly the
-        # accumulator, the input ciphertext limb and the output
-        "k_moddown": (4 + 6 * (L - 1)) * N * W * B,
-    }.get(cls)
+# ------------------------------------------------------------------------------------------- the BASELINE configs through the plugin
+BACKEND = os.path.join(ROOT, "reference-seal-backend_b200", "backend")
+HARNESS = os.path.join(BACKEND, "mini_harness")
+PLUGIN = os.path.join(BACKEND, "libhebench_seal_backend.so")
+# name -> (BASELINE.json config, harness arguments, timed operate() iterations); shapes are the stated ones
+PLUGIN_CONFIGS = {
+    "C1": ("configs[0]: BFV eltwise multiply ct x ct, N=8192, n=100, 10 x 10 samples", ["--filter", "EltwiseMultiply BFV Offline", "--n", "100", "--samples", "10,10"], 5),
+    "C2add": ("configs[1]: CKKS eltwise add, N=8192 {60,45,60}, 100 x 10 = 1000 results", ["--filter", "EltwiseAdd CKKS Offline", "--n", "1000", "--samples", "100,10"], 5),
+    "C2mul": ("configs[1]: CKKS eltwise multiply (the reference's descriptor: no relinearize / rescale), 1000 results",
+              ["--filter", "EltwiseMultiply CKKS Offline", "--n", "1000", "--samples", "100,10"], 5),
+    "C3": ("configs[2]: CKKS dot product n=100, N=16384 {60,40,60}, 100 x 100 = 10^4 results",
+           ["--filter", "DotProduct CKKS Offline", "--n", "100", "--poly", "16384", "--samples", "100,100"], 2),
+    "C5": ("configs[4]: CKKS logistic regression PolyD3, 16 features, N=32768 {60,45x5,60}, batch 1024",
+           ["--filter", "LogisticRegression_PolyD3 CKKS Offline", "--poly", "32768", "--batch", "1024"], 2),
+    "C4row": ("configs[3]: CKKS MatMult Row 100x100x100 (needs N=32768: cols_M0 * cols_M1 <= N/2), depth 3",
+              ["--filter", "MatrixMultiply CKKS Latency other=2", "--dims", "100,100,100", "--poly", "32768", "--depth", "3"], 1),
+    "C4val": ("configs[3]: CKKS MatMult Val 100x100x100, N=16384 {60,45x5,60}",
+              ["--filter", "MatrixMultiply CKKS Latency other=0", "--dims", "100,100,100", "--poly", "16384", "--depth", "6"], 1),
+    "C4cba": ("configs[3]: CKKS MatMult CipherBatchAxis 100x100x100, N=16384 {60,45x5,60} (2 x 10^4 input ciphertexts)",
+              ["--filter", "MatrixMultiply CKKS Latency other=1", "--dims", "100,100,100", "--poly", "16384", "--depth", "6"], 1),
+}
+STRONG_SCALING = ["C3", "C5"]   # fixed work split over N GPUs by the plugin
+
+
+def run_plugin_config(name, gpus, peak_hbm, bf_int_peak, bf_dp_peak, timeout=600):
+    import tempfile
+    desc, hargs, iters = PLUGIN_CONFIGS[name]
+    with tempfile.TemporaryDirectory() as tmp:
+        jpath, ppath = os.path.join(tmp, "harness.json"), os.path.join(tmp, "profile.json")
+        env = dict(os.environ, HEB_B200_SEED=str(SEED), HEB_B200_GPUS=str(gpus), HEB_B200_PROFILE_JSON=ppath, HEB_B200_PROFILE_SKIP=str(1 + iters))
+        env.pop("OMP_NUM_THREADS", None)   # torchrun pins it to 1; the host phases (encode / encrypt / decrypt) use every core
+        t0 = time.time()
+        try:
+            p = subprocess.run([HARNESS, "--backend_lib_path", PLUGIN, "--iterations", str(iters), "--extra-operate", "1", "--json", jpath] + hargs,
+                               capture_output=True, text=True, env=env, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            return {"config": desc, "error": f"timeout after {timeout} s"}
+        wall = time.time() - t0
+        if "Failed: 0" not in p.stdout or not os.path.exists(jpath):
+            return {"config": desc, "error": (p.stdout[-400:] + p.stderr[-400:]).strip()}
+        with open(jpath) as f:
+            h = json.loads(f.readline())
+        prof = None
+        if os.path.exists(ppath):
+            with open(ppath) as f:
+                prof = json.loads(f.readline())
+    n = h["results_per_operate"]
+    op_ms = h["operate_ms"]
+    e2e_ms = h["load_ms"] + op_ms + h["store_ms"]
+    out = {"config": desc, "gpus": gpus, "results_per_operate": n, "validated": h["validated"], "operate_ms": op_ms,
+           "samples_per_s": n / (op_ms / 1e3), "load_ms": h["load_ms"], "store_ms": h["store_ms"],
+           "e2e_samples_per_s": n / (e2e_ms / 1e3), "e2e_ms": e2e_ms,
+           "e2e_path": "libhebench_seal_backend.so load -> operate -> store, pageable host ciphertexts",
+           "host_ms": {k: h[k] for k in ("encode_ms", "encrypt_ms", "decrypt_ms", "decode_ms")}, "harness_wall_s": wall}
+    if prof:
+        ks = prof["kernels"]
+        tot = sum(v["ms_sum_over_gpus"] for v in ks.values())
+        top = max(ks, key=lambda k: ks[k]["ms_sum_over_gpus"])
+        def frac(v):
+            sec = v["ms_sum_over_gpus"] / 1e3
+            floor_s = v["bfly_int"] / bf_int_peak + v["bfly_fp64"] / bf_dp_peak
+            return {"ms": v["ms_sum_over_gpus"] / max(prof["gpus"], 1), "share": v["ms_sum_over_gpus"] / tot if tot else None,
+                    "hbm_frac": v["bytes"] / sec / 1e9 / peak_hbm if sec > 0 else None, "pipe_frac": floor_s / sec if sec > 0 and floor_s > 0 else None}
+        out["dominant_kernel"] = top
+        out["dominant"] = frac(ks[top])
+        out["kernels"] = {k: frac(v) for k, v in sorted(ks.items(), key=lambda kv: -kv[1]["ms_sum_over_gpus"])}
+        # whole operate(): the time its butterflies and its bytes need at the measured peaks / the profiled kernel time
+        floor_pipe = sum(v["bfly_int"] / bf_int_peak + v["bfly_fp64"] / bf_dp_peak for v in ks.values())
+        floor_hbm = sum(v["bytes"] for v in ks.values()) / (peak_hbm * 1e9)
+        out["operate_roofline"] = {"kernel_ms": tot / max(prof["gpus"], 1), "pipe_floor_ms": floor_pipe * 1e3 / max(prof["gpus"], 1),
+                                   "hbm_floor_ms": floor_hbm * 1e3 / max(prof["gpus"], 1),
+                                   "frac_of_binding_floor": max(floor_pipe, floor_hbm) * 1e3 / tot if tot else None}
+    return out
+
+
+def run_plugin_configs(names, gpus, peak_hbm, bf_int_peak, bf_dp_peak, budget_s):
+    out, t0 = {}, time.time()
+    if not (os.path.exists(HARNESS) and os.path.exists(PLUGIN)):
+        return {"error": "plugin / mini harness not built (python -c 'import __graft_entry__ as g; g.build()')"}
+    for name in names:
+        if time.time() - t0 > budget_s:
+            out[name] = {"config": PLUGIN_CONFIGS[name][0], "skipped": f"time budget of {budget_s:.0f} s for the configs block used up"}
+            continue
+        out[name] = run_plugin_config(name, gpus, peak_hbm, bf_int_peak, bf_dp_peak)
+    return out
 
 
 def run_b200(args):

@@ -79,6 +79,11 @@ int b200he_batch_download_async(const b200he_batch *b, uint64_t first, uint64_t 
  * stream); download returns when every host[i] is complete. */
 int b200he_batch_upload_scattered(b200he_batch *b, uint64_t first, uint64_t n, const uint64_t *const *host);
 int b200he_batch_download_scattered(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *const *host);
+/* dst (a batch of any context, any GPU) = a copy of src (another context / another GPU): device to device over NVLink
+ * (cudaMemcpyPeerAsync), stream-ordered on both contexts, no host round trip and no wait.  The one exchange step of the
+ * path: the per-GPU partial sums of logistic regression's collapse meet on GPU 0
+ * (R/src/engine/seal_context.cpp:397-400 is the reference's mutex-guarded add_inplace). */
+int b200he_batch_copy_from(b200he_batch *dst, const b200he_batch *src);
 uint64_t b200he_batch_count(const b200he_batch *b);
 int b200he_batch_size(const b200he_batch *b);
 int b200he_batch_level(const b200he_batch *b);      /* L = number of RNS limbs */
@@ -99,6 +104,14 @@ int b200he_sub(b200he_ctx *ctx, const b200he_batch *a, const uint32_t *ai, const
  * R/src/benchmarks/ckks/seal_ckks_dot_product_benchmark.cpp:325, R/src/engine/seal_context.cpp:446 */
 int b200he_multiply(b200he_ctx *ctx, const b200he_batch *a, const uint32_t *ai, const b200he_batch *b, const uint32_t *bi,
                     uint64_t n, b200he_batch *out);
+/* The inner loop of MatMult CipherBatchAxis: a = `rows x inner` matrix of ciphertexts (row-major), bt = the right-hand
+ * `inner x cols` matrix stored by COLUMNS (`cols x inner`: a row of a and a column of b are both contiguous runs);
+ * out[i * cols + j] = sum_k a[i * inner + k] * bt[j * inner + k] as size-3 ciphertexts -- `inner` Evaluator::multiply calls
+ * and inner - 1 Evaluator::add_inplace calls per cell in the reference, one pass with register accumulators here; same
+ * bits (sums of residues are exact).  CKKS, NTT form, out must not alias an input.
+ * R/src/benchmarks/ckks/seal_ckks_matmult_cipherbatchaxis_benchmark.cpp:385-422 */
+int b200he_matmul_accumulate(b200he_ctx *ctx, const b200he_batch *a, const b200he_batch *bt, uint64_t rows, uint64_t inner,
+                             uint64_t cols, b200he_batch *out);
 /* Evaluator::relinearize_inplace (size 3 -> 2; size 2 is a no-op copy)  (out may alias in)
  * R/src/benchmarks/ckks/seal_ckks_dot_product_benchmark.cpp:329, R/src/engine/seal_context.cpp:390,447 */
 int b200he_relinearize(b200he_ctx *ctx, const b200he_batch *in, b200he_batch *out);
@@ -145,7 +158,7 @@ int b200he_ntt_inverse(b200he_ctx *ctx, const b200he_batch *in, b200he_batch *ou
 
 /* ---- measurement hooks ---- */
 enum {
-    B200HE_KERN_NTT_FWD = 0, B200HE_KERN_NTT_INV, B200HE_KERN_NTT_INV_TAIL, B200HE_KERN_KS_INNER, B200HE_KERN_MODDOWN,
+    B200HE_KERN_NTT_FWD = 0, B200HE_KERN_NTT_INV, B200HE_KERN_TENSOR_MAC, B200HE_KERN_KS_INNER, B200HE_KERN_MODDOWN,
     B200HE_KERN_ELEMENTWISE, B200HE_KERN_TENSOR, B200HE_KERN_GALOIS, B200HE_KERN_COPY, B200HE_KERN_BEHZ, B200HE_KERN_COUNT
 };
 /* kernels launched by this context since creation */
@@ -154,6 +167,11 @@ uint64_t b200he_launch_count(const b200he_ctx *ctx);
  * returns accumulated milliseconds and launch counts per class (arrays of B200HE_KERN_COUNT) */
 int b200he_profile_begin(b200he_ctx *ctx);
 int b200he_profile_end(b200he_ctx *ctx, double *ms, uint64_t *launches);
+/* algorithmic work of the launches recorded between profile_begin and profile_end, per kernel class (arrays of
+ * B200HE_KERN_COUNT; valid until the next profile_begin): modular-butterfly equivalents executed on the integer pipe and on
+ * the FP64 pipe (the unit the pipes' peaks are measured in), and the bytes that have to cross HBM.  The
+ * roofline fractions of ANY workload follow from these and the measured times, without per-workload formulas. */
+int b200he_profile_work(const b200he_ctx *ctx, double *bfly_int, double *bfly_fp64, double *bytes);
 const char *b200he_kernel_name(int kern_class);
 
 #ifdef __cplusplus

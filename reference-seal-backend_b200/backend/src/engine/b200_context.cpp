@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <sstream>
+#include <thread>
 
 #include "../../hostfhe/hostfhe.h"
 
@@ -52,6 +54,8 @@ void SEALContextWrapper::init(bool ckks, std::size_t N, std::size_t depth, int c
     m_K          = depth + 1;
     m_scale_bits = scale_or_plain_bits;
     if (const char *e = getenv("HEB_B200_TRACE_DIR")) m_trace_dir = e;
+    if (const char *e = getenv("HEB_B200_PROFILE_JSON")) m_profile_path = e;
+    if (const char *e = getenv("HEB_B200_PROFILE_SKIP")) m_profile_skip = atol(e);
     // key material and encryption randomness come from OS entropy (seed 0) unless HEB_B200_SEED fixes them: reproducible
     // keys and encryptions are for the parity tests and benchmarks only
     std::uint64_t seed = 0;
@@ -226,19 +230,28 @@ std::vector<std::uint64_t> SEALContextWrapper::partition(std::uint64_t n) const
 
 DeviceBatchPtr SEALContextWrapper::upload(int g, const std::vector<Ciphertext> &src, std::size_t first, std::size_t n) const
 {
-    DeviceBatchPtr b = newBatch(g);
     if (first + n > src.size()) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("upload range out of bounds"), HEBENCH_ECODE_INVALID_ARGS);
+    std::vector<std::size_t> items(n);
+    std::iota(items.begin(), items.end(), first);
+    return upload(g, src, items);
+}
+DeviceBatchPtr SEALContextWrapper::upload(int g, const std::vector<Ciphertext> &src, const std::vector<std::size_t> &items) const
+{
+    DeviceBatchPtr b    = newBatch(g);
+    const std::size_t n = items.size();
     if (n == 0) {
         check(b200he_batch_resize(b->get(), 0, 2, (int)topLevel(), m_ckks, m_scale), "b200he_batch_resize");
         return b;
     }
-    const Ciphertext &c0 = src[first];
+    for (std::size_t i : items)
+        if (i >= src.size()) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("upload item out of bounds"), HEBENCH_ECODE_INVALID_ARGS);
+    const Ciphertext &c0 = src[items[0]];
     check(b200he_batch_resize(b->get(), n, c0.size, c0.L, c0.ntt, c0.scale), "b200he_batch_resize");
-    // one call for the whole range: the library gathers the separately allocated ciphertexts into pinned staging
+    // one call for the whole list: the library gathers the separately allocated ciphertexts into pinned staging
     // buffers on a few host threads while the previous chunk crosses PCIe, and returns once every source has been read
     std::vector<const std::uint64_t *> ptrs(n);
     for (std::size_t i = 0; i < n; ++i) {
-        const Ciphertext &c = src[first + i];
+        const Ciphertext &c = src[items[i]];
         if (c.size != c0.size || c.L != c0.L || c.ntt != c0.ntt)
             throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("ciphertexts of one batch must share size, level and form"), HEBENCH_ECODE_INVALID_ARGS);
         ptrs[i] = c.data.data();
@@ -290,6 +303,153 @@ void SEALContextWrapper::syncAll() const
     for (b200he_ctx *c : m_dev) check(b200he_ctx_sync(c), "b200he_ctx_sync");
 }
 
+void SEALContextWrapper::beginOperate()
+{
+    m_profiling = !m_profile_path.empty() && m_operate_calls >= m_profile_skip;
+    ++m_operate_calls;
+    if (m_profiling)
+        for (b200he_ctx *c : m_dev) check(b200he_profile_begin(c), "b200he_profile_begin");
+}
+void SEALContextWrapper::endOperate(std::uint64_t results)
+{
+    syncAll();
+    if (!m_profiling) return;
+    double ms[B200HE_KERN_COUNT] = {}, wi[B200HE_KERN_COUNT] = {}, wd[B200HE_KERN_COUNT] = {}, wb[B200HE_KERN_COUNT] = {}, ms_max[B200HE_KERN_COUNT] = {};
+    std::uint64_t launches[B200HE_KERN_COUNT] = {};
+    for (b200he_ctx *c : m_dev) {
+        double m1[B200HE_KERN_COUNT], a[B200HE_KERN_COUNT], b[B200HE_KERN_COUNT], d[B200HE_KERN_COUNT];
+        std::uint64_t l1[B200HE_KERN_COUNT];
+        check(b200he_profile_end(c, m1, l1), "b200he_profile_end");
+        check(b200he_profile_work(c, a, b, d), "b200he_profile_work");
+        for (int i = 0; i < B200HE_KERN_COUNT; ++i) {
+            ms[i] += m1[i];
+            ms_max[i] = std::max(ms_max[i], m1[i]);
+            launches[i] += l1[i];
+            wi[i] += a[i];
+            wd[i] += b[i];
+            wb[i] += d[i];
+        }
+    }
+    m_profiling = false;
+    FILE *f = fopen(m_profile_path.c_str(), "a");
+    if (!f) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("HEB_B200_PROFILE_JSON: cannot write " + m_profile_path), HEBENCH_ECODE_CRITICAL_ERROR);
+    fprintf(f, "{\"operate_call\": %ld, \"gpus\": %d, \"results\": %llu, \"kernels\": {", m_operate_calls - 1, gpuCount(), (unsigned long long)results);
+    bool first = true;
+    for (int i = 0; i < B200HE_KERN_COUNT; ++i) {
+        if (!launches[i]) continue;
+        fprintf(f, "%s\"%s\": {\"ms_sum_over_gpus\": %.6f, \"ms_max_over_gpus\": %.6f, \"launches\": %llu, \"bfly_int\": %.6e, \"bfly_fp64\": %.6e, \"bytes\": %.6e}",
+                first ? "" : ", ", b200he_kernel_name(i), ms[i], ms_max[i], (unsigned long long)launches[i], wi[i], wd[i], wb[i]);
+        first = false;
+    }
+    fprintf(f, "}}\n");
+    fclose(f);
+}
+
+void SEALContextWrapper::forEachGpu(const std::function<void(int)> &fn) const
+{
+    const int n = gpuCount();
+    if (n == 1) {
+        fn(0);
+        return;
+    }
+    std::vector<std::exception_ptr> err(n);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n; ++g)
+        th.emplace_back([&, g]() {
+            try {
+                fn(g);
+            } catch (...) {
+                err[g] = std::current_exception();
+            }
+        });
+    for (std::thread &t : th) t.join();
+    for (const std::exception_ptr &e : err)
+        if (e) std::rethrow_exception(e);
+}
+
+GridOperands SEALContextWrapper::loadGrid(const std::vector<Ciphertext> &src0, std::size_t unit0, const std::vector<Ciphertext> &src1, std::size_t unit1,
+                                          const std::function<std::vector<std::size_t>(std::size_t)> &items1) const
+{
+    GridOperands out;
+    const std::vector<Ciphertext> *src[2] = { &src0, &src1 };
+    const std::size_t unit[2] = { unit0 ? unit0 : 1, unit1 ? unit1 : 1 };
+    const std::size_t n_items[2] = { src0.size() / unit[0], src1.size() / unit[1] };
+    out.split = n_items[1] > n_items[0] ? 1 : 0;
+    const int G = gpuCount();
+    for (int p = 0; p < 2; ++p) {
+        ShardedCiphertexts &s = out.p[p];
+        s.n_total    = n_items[p];
+        s.replicated = p != out.split;
+        s.first      = s.replicated ? std::vector<std::uint64_t>(G + 1, n_items[p]) : partition(n_items[p]);
+        if (s.replicated) s.first[0] = 0;
+        s.shard.resize(G);
+    }
+    forEachGpu([&](int g) {
+        for (int p = 0; p < 2; ++p) {
+            ShardedCiphertexts &s     = out.p[p];
+            const std::uint64_t first = s.replicated ? 0 : s.first[g], last = s.replicated ? n_items[p] : s.first[g + 1];
+            std::vector<std::size_t> items;
+            for (std::uint64_t it = first; it < last; ++it) {
+                if (p == 1 && items1) {
+                    const std::vector<std::size_t> v = items1(it);
+                    items.insert(items.end(), v.begin(), v.end());
+                } else
+                    for (std::size_t u = 0; u < unit[p]; ++u) items.push_back(it * unit[p] + u);
+            }
+            s.shard[g] = upload(g, *src[p], items);
+        }
+    });
+    return out;
+}
+
+GridShare SEALContextWrapper::gridShare(const GridOperands &in, int g, const std::uint64_t v0[2], const std::uint64_t b[2]) const
+{
+    GridShare sh;
+    const int s = in.split;
+    // the requested range of the split operand that lives on this GPU
+    const std::uint64_t f = in.p[s].first[g], l = in.p[s].first[g + 1];
+    const std::uint64_t lo = std::max<std::uint64_t>(f, v0[s]), hi = std::min<std::uint64_t>(l, v0[s] + b[s]);
+    if (hi <= lo) return sh;
+    const std::uint64_t nb = hi - lo, n = nb * b[1 - s];
+    sh.ai.resize(n);
+    sh.bi.resize(n);
+    sh.result.resize(n);
+    for (std::uint64_t k = 0; k < n; ++k) {
+        std::uint64_t i, j;   // global item indices
+        if (s == 0) {
+            i = lo + k / b[1];
+            j = v0[1] + k % b[1];
+        } else {
+            i = v0[0] + k / nb;
+            j = lo + k % nb;
+        }
+        sh.ai[k]     = (std::uint32_t)(s == 0 ? i - f : i);
+        sh.bi[k]     = (std::uint32_t)(s == 1 ? j - f : j);
+        sh.result[k] = (i - v0[0]) * b[1] + (j - v0[1]);
+    }
+    return sh;
+}
+
+std::vector<Ciphertext> SEALContextWrapper::gather(const ShardedCiphertexts &src) const
+{
+    std::vector<Ciphertext> out(src.total());
+    std::vector<std::vector<Ciphertext>> part(src.shard.size());
+    if (src.replicated) {
+        if (!src.shard.empty()) out = download(*src.shard[0]);
+        return out;
+    }
+    forEachGpu([&](int g) {
+        if ((std::size_t)g < src.shard.size() && src.shard[g] && src.shard[g]->count() > 0) part[g] = download(*src.shard[g]);
+    });
+    for (std::size_t g = 0; g < part.size(); ++g)
+        for (std::size_t k = 0; k < part[g].size(); ++k) {
+            const std::uint64_t id = src.ids.empty() ? src.first[g] + k : src.ids[g][k];
+            if (id >= out.size()) throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("result index out of range"), HEBENCH_ECODE_CRITICAL_ERROR);
+            out[id] = std::move(part[g][k]);
+        }
+    return out;
+}
+
 // R/src/engine/seal_context.cpp:255-263: the ciphertext with more limbs is switched down (CKKS: limbs dropped)
 void SEALContextWrapper::matchLevel(DeviceBatch &a, DeviceBatch &b) const
 {
@@ -312,9 +472,12 @@ void SEALContextWrapper::accumulateCKKS(DeviceBatch &cipher, std::size_t count) 
 DeviceBatchPtr SEALContextWrapper::maskBatch(int g, std::size_t first_index, std::size_t n, std::size_t total, int level)
 {
     std::ostringstream key;
-    key << g << ':' << first_index << ':' << n << ':' << total << ':' << level;
-    auto it = m_mask_cache.find(key.str());
-    if (it != m_mask_cache.end()) return it->second;
+    key << "mask:" << g << ':' << first_index << ':' << n << ':' << total << ':' << level;
+    {
+        std::lock_guard<std::mutex> lock(m_cache_mtx);
+        auto it = m_mask_cache.find(key.str());
+        if (it != m_mask_cache.end()) return it->second;
+    }
     std::vector<Plaintext> masks(n);
 #pragma omp parallel for
     for (long i = 0; i < (long)n; ++i) {
@@ -326,12 +489,33 @@ DeviceBatchPtr SEALContextWrapper::maskBatch(int g, std::size_t first_index, std
         masks[i] = std::move(p);
     }
     DeviceBatchPtr b = uploadPlain(g, masks);
+    std::lock_guard<std::mutex> lock(m_cache_mtx);
+    m_mask_cache[key.str()] = b;
+    return b;
+}
+
+// coefficient plaintext `index` of a Horner evaluation switched down to `level` (mod_switch_to_inplace(plain): the
+// trailing limbs dropped, R/src/engine/seal_context.cpp:451), resident on GPU g; deterministic, so cached
+DeviceBatchPtr SEALContextWrapper::coeffBatch(int g, const std::vector<Plaintext> &plain_coefficients, std::size_t index, int level)
+{
+    std::ostringstream key;
+    key << "coeff:" << g << ':' << index << ':' << level << ':' << (const void *)plain_coefficients.data();
+    {
+        std::lock_guard<std::mutex> lock(m_cache_mtx);
+        auto it = m_mask_cache.find(key.str());
+        if (it != m_mask_cache.end()) return it->second;
+    }
+    Plaintext p = plain_coefficients.at(index);
+    p.data.resize((std::size_t)level * m_N);
+    p.L              = level;
+    DeviceBatchPtr b = uploadPlain(g, std::vector<Plaintext>(1, p));
+    std::lock_guard<std::mutex> lock(m_cache_mtx);
     m_mask_cache[key.str()] = b;
     return b;
 }
 
 // R/src/engine/seal_context.cpp:349-415 on one GPU's shard of the samples
-DeviceBatchPtr SEALContextWrapper::collapseCKKS(DeviceBatch &ciphers, std::size_t first_index, std::size_t total, bool add_encrypted_zero)
+DeviceBatchPtr SEALContextWrapper::collapseCKKS(DeviceBatch &ciphers, std::size_t first_index, std::size_t total, const Ciphertext *encrypted_zero)
 {
     b200he_ctx *c = ciphers.ctx();
     int g = 0;
@@ -350,12 +534,11 @@ DeviceBatchPtr SEALContextWrapper::collapseCKKS(DeviceBatch &ciphers, std::size_
         check(b200he_batch_set_scale(ciphers.get(), m_scale), "b200he_batch_set_scale");
         check(b200he_sum(c, ciphers.get(), result->get()), "b200he_sum");
     }
-    if (add_encrypted_zero) {
-        // retval = Enc(0) at the top level, switched down to the summands' level, scale forced (:360-361, :397-400)
-        Plaintext zero = encodeVector(std::vector<double>(1, 0.0), m_scale);
-        const Ciphertext zc = encrypt(zero);
-        trace("collapse_zero", zc);
-        DeviceBatchPtr z = upload(g, zc);
+    if (encrypted_zero) {
+        // retval = Enc(0) at the top level, switched down to the summands' level, scale forced (:360-361, :397-400).  The
+        // encryption itself was drawn ahead of this call (LogRegHornerBenchmark::freshEncryptions); the upload only stages.
+        trace("collapse_zero", *encrypted_zero);
+        DeviceBatchPtr z = upload(g, *encrypted_zero);
         if (n > 0) {
             check(b200he_mod_drop(c, z->get(), result->level(), z->get()), "b200he_mod_drop");
             check(b200he_batch_set_scale(z->get(), result->scale()), "b200he_batch_set_scale");
@@ -367,7 +550,7 @@ DeviceBatchPtr SEALContextWrapper::collapseCKKS(DeviceBatch &ciphers, std::size_
 }
 
 // R/src/engine/seal_context.cpp:417-458 (Horner), cipher_input and the result are single-ciphertext batches
-DeviceBatchPtr SEALContextWrapper::evaluatePolynomial(DeviceBatch &cipher_input, const std::vector<Plaintext> &plain_coefficients)
+DeviceBatchPtr SEALContextWrapper::evaluatePolynomial(DeviceBatch &cipher_input, const std::vector<Plaintext> &plain_coefficients, const Ciphertext &seed)
 {
     if (plain_coefficients.empty())
         throw hebench::cpp::HEBenchError(HEBERROR_MSG_CLASS("Polynomial must have, at least, 1 coefficient."), HEBENCH_ECODE_INVALID_ARGS);
@@ -375,19 +558,15 @@ DeviceBatchPtr SEALContextWrapper::evaluatePolynomial(DeviceBatch &cipher_input,
     int g = 0;
     for (std::size_t i = 0; i < m_dev.size(); ++i)
         if (m_dev[i] == c) g = (int)i;
-    auto it = plain_coefficients.rbegin();
-    const Ciphertext seed = encrypt(*it);
     trace("horner_seed", seed);
-    DeviceBatchPtr retval = upload(g, seed);
-    for (++it; it != plain_coefficients.rend(); ++it) {
+    DeviceBatchPtr retval = upload(g, seed);   // Enc(a_d), drawn ahead of the call
+    for (std::size_t k = plain_coefficients.size() - 1; k-- > 0;) {
         matchLevel(cipher_input, *retval);
         check(b200he_multiply(c, retval->get(), nullptr, cipher_input.get(), nullptr, 1, retval->get()), "b200he_multiply");
         check(b200he_relinearize_rescale(c, retval->get(), retval->get()), "b200he_relinearize_rescale");
-        Plaintext p = *it;   // mod_switch_to_inplace(plain, retval.parms_id())
-        p.data.resize((std::size_t)retval->level() * m_N);
-        p.L = retval->level();
-        DeviceBatchPtr dp = uploadPlain(g, std::vector<Plaintext>(1, p));
-        check(b200he_batch_set_scale(retval->get(), p.scale), "b200he_batch_set_scale");
+        // mod_switch_to_inplace(plain, retval.parms_id()); scale forced (:451-452)
+        DeviceBatchPtr dp = coeffBatch(g, plain_coefficients, k, retval->level());
+        check(b200he_batch_set_scale(retval->get(), plain_coefficients[k].scale), "b200he_batch_set_scale");
         check(b200he_add_plain(c, retval->get(), dp->get(), nullptr, retval->get()), "b200he_add_plain");
     }
     return retval;

@@ -7,6 +7,8 @@
 //
 //   mini_harness --backend_lib_path libhebench_seal_backend.so [--random_seed 1234] [--filter TEXT] [--list]
 //                [--samples A,B] [--batch N] [--iterations K] [--n N] [--dims R,C0,C1] [--poly N] [--depth D] [--csv FILE]
+//                [--json FILE]          one JSON object per benchmark: wall time of every phase (encode ... decode), every timed operate()
+//                [--extra-operate K]    K more untimed operate() calls after the timed ones (the backend profiles those, HEB_B200_PROFILE_*)
 #include <dlfcn.h>
 
 #include <chrono>
@@ -28,10 +30,10 @@ using namespace hebench::APIBridge;
     if (!p_##name) { fprintf(stderr, "missing symbol %s\n", #name); return 2; }
 
 struct Options {
-    std::string lib, filter, csv;
+    std::string lib, filter, csv, json;
     unsigned seed = 1234;
     bool list = false;
-    uint64_t samples[2] = { 2, 3 }, batch = 8, iterations = 2, n = 0, dims[3] = { 0, 0, 0 }, poly = 0, depth = 0;
+    uint64_t samples[2] = { 2, 3 }, batch = 8, iterations = 2, n = 0, dims[3] = { 0, 0, 0 }, poly = 0, depth = 0, extra_operate = 0;
 };
 
 static const char *workloadName(Workload w)
@@ -95,6 +97,8 @@ int main(int argc, char **argv)
         else if (a == "--random_seed") o.seed = (unsigned)atol(next().c_str());
         else if (a == "--filter") o.filter = next();
         else if (a == "--csv") o.csv = next();
+        else if (a == "--json") o.json = next();
+        else if (a == "--extra-operate") o.extra_operate = strtoull(next().c_str(), nullptr, 10);
         else if (a == "--list") o.list = true;
         else if (a == "--samples") sscanf(next().c_str(), "%lu,%lu", &o.samples[0], &o.samples[1]);
         else if (a == "--batch") o.batch = strtoull(next().c_str(), nullptr, 10);
@@ -131,6 +135,8 @@ int main(int argc, char **argv)
         csv.open(o.csv);
         csv << "index,workload,scheme,category,other,params,results_per_operate,operate_ms,samples_per_s,load_ms,store_ms,validated,failed_values\n";
     }
+    std::ofstream json;
+    if (!o.json.empty()) json.open(o.json);
     std::mt19937_64 rng(o.seed);
     uint64_t failed = 0, ran = 0;
     for (uint64_t bi = 0; bi < count; ++bi) {
@@ -255,28 +261,43 @@ int main(int argc, char **argv)
         };
         Handle h_enc{}, h_cipher{}, h_remote{}, h_result{}, h_local{}, h_plain{};
         bool ok = true;
-        double t_load = 0, t_op = 0, t_store = 0;
+        double t_load = 0, t_op = 0, t_store = 0, t_encode = 0, t_encrypt = 0, t_decrypt = 0, t_decode = 0, t_warm = 0;
+        std::vector<double> t_ops;
         do {
+            auto e0 = std::chrono::steady_clock::now();
             if (p_encode(bench, &in.coll, &h_enc)) { ok = false; break; }
+            auto e1 = std::chrono::steady_clock::now();
             if (p_encrypt(bench, h_enc, &h_cipher)) { ok = false; break; }
             auto t0 = std::chrono::steady_clock::now();
+            t_encode  = ms(e0, e1);
+            t_encrypt = ms(e1, t0);
             if (p_load(bench, &h_cipher, 1, &h_remote)) { ok = false; break; }
             auto t1 = std::chrono::steady_clock::now();
             t_load  = ms(t0, t1);
             if (p_operate(bench, h_remote, idx.data(), idx.size(), &h_result)) { ok = false; break; }   // warm-up
+            t_warm = ms(t1, std::chrono::steady_clock::now());
             for (uint64_t it = 0; it < o.iterations; ++it) {
                 p_destroyHandle(h_result);
                 auto a = std::chrono::steady_clock::now();
                 if (p_operate(bench, h_remote, idx.data(), idx.size(), &h_result)) { ok = false; break; }
-                t_op += ms(a, std::chrono::steady_clock::now());
+                t_ops.push_back(ms(a, std::chrono::steady_clock::now()));
+                t_op += t_ops.back();
+            }
+            for (uint64_t it = 0; ok && it < o.extra_operate; ++it) {   // untimed: the backend's profiled calls
+                p_destroyHandle(h_result);
+                if (p_operate(bench, h_remote, idx.data(), idx.size(), &h_result)) ok = false;
             }
             if (!ok) break;
             t_op /= (double)std::max<uint64_t>(1, o.iterations);
             auto t2 = std::chrono::steady_clock::now();
             if (p_store(bench, h_result, &h_local, 1)) { ok = false; break; }
-            t_store = ms(t2, std::chrono::steady_clock::now());
+            auto t3 = std::chrono::steady_clock::now();
+            t_store = ms(t2, t3);
             if (p_decrypt(bench, h_local, &h_plain)) { ok = false; break; }
+            auto t4 = std::chrono::steady_clock::now();
             if (p_decode(bench, h_plain, &out.coll)) { ok = false; break; }
+            t_decrypt = ms(t3, t4);
+            t_decode  = ms(t4, std::chrono::steady_clock::now());
         } while (false);
         uint64_t bad = 0;
         if (!ok) {
@@ -299,6 +320,16 @@ int main(int argc, char **argv)
             csv << bi << ',' << workloadName(bd.workload) << ',' << scheme << ',' << (bd.category == Latency ? "Latency" : "Offline") << ',' << bd.other << ',';
             for (auto &p : wp) csv << p.name << '=' << p.u_param << ' ';
             csv << ',' << results << ',' << t_op << ',' << sps << ',' << t_load << ',' << t_store << ',' << (ok ? 1 : 0) << ',' << bad << '\n';
+        }
+        if (json.is_open()) {
+            json << "{\"index\": " << bi << ", \"title\": \"" << title.str() << "\", \"params\": {";
+            for (size_t k = 0; k < wp.size(); ++k) json << (k ? ", " : "") << "\"" << wp[k].name << "\": " << wp[k].u_param;
+            json << "}, \"results_per_operate\": " << results << ", \"validated\": " << (bad ? "false" : "true") << ", \"failed_values\": " << bad
+                 << ", \"encode_ms\": " << t_encode << ", \"encrypt_ms\": " << t_encrypt << ", \"load_ms\": " << t_load << ", \"warmup_operate_ms\": " << t_warm
+                 << ", \"operate_ms\": " << t_op << ", \"operate_ms_all\": [";
+            for (size_t k = 0; k < t_ops.size(); ++k) json << (k ? ", " : "") << t_ops[k];
+            json << "], \"store_ms\": " << t_store << ", \"decrypt_ms\": " << t_decrypt << ", \"decode_ms\": " << t_decode << "}\n";
+            json.flush();
         }
         if (bad) ++failed;
         for (Handle h : { h_plain, h_local, h_result, h_remote, h_cipher, h_enc, bench })

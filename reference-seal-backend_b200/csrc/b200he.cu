@@ -122,10 +122,17 @@ struct b200he_ctx {
     u64 workspace = u64(2) << 30;
     u64 *relin = nullptr;
     std::map<u32, u64 *> gal;
-    std::map<u32, u32 *> galtab;
+    struct GalTab {
+        u32 *d = nullptr;                           // device copy of the NTT-form permutation table [N]
+        unsigned char chunk[4] = { 0, 0, 0, 0 };    // source chunk (2^lognl coefficients) of every output chunk
+    };
+    std::map<u32, GalTab> galtab;
     uint64_t launches = 0;
     bool prof = false;
     std::vector<ProfRec> recs;
+    // algorithmic work of the launches recorded while profiling (b200he_profile_work): butterfly-equivalents on the
+    // integer pipe / on the FP64 pipe, and bytes that have to cross HBM, per kernel class
+    double work_int[B200HE_KERN_COUNT] = {}, work_dp[B200HE_KERN_COUNT] = {}, work_bytes[B200HE_KERN_COUNT] = {};
     Behz behz{};   // BFV only
     int nBsk = 0;
     // pinned staging of b200he_batch_{upload,download}_scattered: two buffers, each guarded by the event of the last
@@ -155,6 +162,16 @@ static inline void prof_pre(b200he_ctx *c, int cls)
         cudaEventRecord(r.a, c->stream);
         c->recs.push_back(r);
     }
+}
+// Work accounting (only while profiling).  Units: one "butterfly-equivalent" = one 64-bit modular multiply by a constant
+// with its add/sub (a Shoup butterfly: the unit tools/imad_peak.cu and tools/fp64_peak.cu measure the pipes in); a
+// 64 x 64 -> 128 multiply-accumulate of k_tensor_mac counts 0.5, a Barrett data x data product 1.5.
+static inline double bfly_per_limb(const b200he_ctx *c) { return 0.5 * c->N * c->logn; }
+static inline void work_add(b200he_ctx *c, int cls, int mod_id, double bf, double bytes)
+{
+    if (!c->prof) return;
+    (c->mods[mod_id].dp ? c->work_dp : c->work_int)[cls] += bf;
+    c->work_bytes[cls] += bytes;
 }
 static inline void prof_post(b200he_ctx *c)
 {
@@ -391,7 +408,7 @@ extern "C" void b200he_ctx_destroy(b200he_ctx *c)
     for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->relin) cudaFree(c->relin);
     for (auto &kv : c->gal) cudaFree(kv.second);
-    for (auto &kv : c->galtab) cudaFree(kv.second);
+    for (auto &kv : c->galtab) cudaFree(kv.second.d);
     c->pool.release();
     for (auto &kv : c->pool.sizes) cudaFree(kv.first);   // blocks still held by undestroyed batches
     if (c->d_tables) cudaFree(c->d_tables);
@@ -460,13 +477,20 @@ static int upload_key(b200he_ctx *c, u64 *d, const uint64_t *key)
     return 0;
 }
 
+static int galois_table(b200he_ctx *c, u32 elt, const b200he_ctx::GalTab **out);
+
 extern "C" int b200he_set_relin_key(b200he_ctx *c, const uint64_t *key)
 {
     if (!c || !key) return fail("set_relin_key: NULL argument");
     if (c->K < 2) return fail("set_relin_key: context has no special prime (K < 2)");
     CK(cudaSetDevice(c->device));
-    if (!c->relin) CK(cudaMalloc((void **)&c->relin, 2 * key_words(c) * 8));
-    return upload_key(c, c->relin, key);
+    // the key is published only once it is valid and resident: a rejected upload leaves the previous state untouched
+    u64 *d = nullptr;
+    CK(cudaMalloc((void **)&d, 2 * key_words(c) * 8));
+    if (int rc = upload_key(c, d, key)) { cudaFree(d); return rc; }
+    if (c->relin) cudaFree(c->relin);   // (upload_key has synchronised the stream: nothing in flight reads the old key)
+    c->relin = d;
+    return 0;
 }
 extern "C" int b200he_set_galois_key(b200he_ctx *c, uint32_t elt, const uint64_t *key)
 {
@@ -474,14 +498,22 @@ extern "C" int b200he_set_galois_key(b200he_ctx *c, uint32_t elt, const uint64_t
     if (c->K < 2) return fail("set_galois_key: context has no special prime (K < 2)");
     if (!(elt & 1) || elt >= 2 * c->N) return fail("set_galois_key: invalid Galois element %u", elt);
     CK(cudaSetDevice(c->device));
-    u64 *&d = c->gal[elt];
-    if (!d) CK(cudaMalloc((void **)&d, 2 * key_words(c) * 8));
-    return upload_key(c, d, key);
+    u64 *d = nullptr;
+    CK(cudaMalloc((void **)&d, 2 * key_words(c) * 8));
+    if (int rc = upload_key(c, d, key)) { cudaFree(d); return rc; }
+    if (c->scheme == B200HE_CKKS) {   // the element's permutation table goes up with its key, not inside the first rotation
+        const b200he_ctx::GalTab *t = nullptr;
+        if (int rc = galois_table(c, elt, &t)) { cudaFree(d); return rc; }
+    }
+    auto it = c->gal.find(elt);
+    if (it != c->gal.end()) { cudaFree(it->second); it->second = d; }
+    else c->gal.emplace(elt, d);
+    return 0;
 }
 extern "C" int b200he_has_galois_key(const b200he_ctx *c, uint32_t elt) { return c && c->gal.count(elt) ? 1 : 0; }
 
 // NTT-form Galois permutation (SEAL GaloisTool::generate_table_ntt): out[i] = in[table[i]]
-static int galois_table(b200he_ctx *c, u32 elt, const u32 **out)
+static int galois_table(b200he_ctx *c, u32 elt, const b200he_ctx::GalTab **out)
 {
     auto it = c->galtab.find(elt);
     if (it == c->galtab.end()) {
@@ -492,16 +524,23 @@ static int galois_table(b200he_ctx *c, u32 elt, const u32 **out)
             const u32 idx = (u32)(((u64)elt * odd) & (2 * (u64)N - 1));
             tab[i] = hm::brv((idx - 1) >> 1, c->logn);
         }
-        u32 *d = nullptr;
-        CK(cudaMalloc((void **)&d, N * sizeof(u32)));
+        b200he_ctx::GalTab t;
+        // the table maps aligned blocks of 2^k indices onto aligned blocks of 2^k indices; the kernels rely on it at
+        // chunk granularity (the chunk an output chunk gathers from) -- checked here rather than assumed
+        const u32 NL = 1u << c->lognl;
+        for (u32 r = 0; r < (N >> c->lognl); r++) {
+            t.chunk[r] = (unsigned char)(tab[r * NL] >> c->lognl);
+            for (u32 i = 0; i < NL; i++)
+                if ((tab[r * NL + i] >> c->lognl) != t.chunk[r]) return fail("galois table of element %u does not map chunks onto chunks", elt);
+        }
+        CK(cudaMalloc((void **)&t.d, N * sizeof(u32)));
         // on the context's stream: a plain cudaMemcpy from pageable memory may return before its DMA (ordered on the
-        // NULL stream, which this non-blocking stream does not wait for) has landed, and the permutation kernel would
-        // read a half-written table the first time an element is used
-        CK(cudaMemcpyAsync(d, tab.data(), N * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        // NULL stream, which this non-blocking stream does not wait for) has landed
+        CK(cudaMemcpyAsync(t.d, tab.data(), N * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        it = c->galtab.emplace(elt, d).first;
+        it = c->galtab.emplace(elt, t).first;
     }
-    *out = it->second;
+    *out = &it->second;
     return 0;
 }
 
@@ -662,6 +701,31 @@ extern "C" int b200he_batch_download_scattered(const b200he_batch *b, uint64_t f
     CK(cudaGetLastError());
     return 0;
 }
+extern "C" int b200he_batch_copy_from(b200he_batch *dst, const b200he_batch *src)
+{
+    if (!dst || !src) return fail("batch_copy_from: NULL argument");
+    if (dst == src) return 0;
+    b200he_ctx *cd = dst->ctx, *cs = src->ctx;
+    if (cd->N != cs->N || cd->K != cs->K || cd->scheme != cs->scheme) return fail("batch_copy_from: contexts differ in parameters");
+    TRY(batch_shape(dst, src->count, src->size, src->L, src->ntt, src->scale));
+    const size_t bytes = (size_t)src->count * src->ct_words() * 8;
+    if (!bytes) return 0;
+    // src's stream has produced the data -> dst's stream copies -> src's stream may reuse the block afterwards
+    cudaEvent_t ready = nullptr, done = nullptr;
+    CK(cudaSetDevice(cs->device));
+    CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(ready, cs->stream));
+    CK(cudaSetDevice(cd->device));
+    CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    CK(cudaStreamWaitEvent(cd->stream, ready, 0));
+    CK(cudaMemcpyPeerAsync(dst->d, cd->device, src->d, cs->device, bytes, cd->stream));
+    CK(cudaEventRecord(done, cd->stream));
+    CK(cudaSetDevice(cs->device));
+    CK(cudaStreamWaitEvent(cs->stream, done, 0));
+    CK(cudaEventDestroy(ready));   // destruction is deferred by the runtime until the event has completed
+    CK(cudaEventDestroy(done));
+    return 0;
+}
 extern "C" uint64_t b200he_batch_count(const b200he_batch *b) { return b ? b->count : 0; }
 extern "C" int b200he_batch_size(const b200he_batch *b) { return b ? b->size : 0; }
 extern "C" int b200he_batch_level(const b200he_batch *b) { return b ? b->L : 0; }
@@ -739,6 +803,13 @@ static void launch_moddown(b200he_ctx *c, ModDownArgs D, size_t polys)
     D.nJsub = D.nJ;
     const int kind = dpmask == 0 ? KIND_INT : dpmask == all ? KIND_DP : KIND_BOTH;
     PROF(c, B200HE_KERN_MODDOWN, launch_moddown_kind(geo(c), kind, c->T, D, polys * D.nJ));
+    if (c->prof) {
+        // per output limb: one transform + the constant multiplies of the epilogue (1, or 3 with the fused rescale);
+        // traffic: the accumulator tile, the output, the addend where there is one, the rounded limb(s) once per polynomial
+        const double N = c->N, mults = D.rp2 ? 3.0 : 1.0, n_add = (D.addend[0] ? 0.5 : 0.0) + (D.addend[1] ? 0.5 : 0.0) + (D.gal ? 0.5 : 0.0);
+        for (int j = 0; j < D.nJ; j++) work_add(c, B200HE_KERN_MODDOWN, j, polys * (bfly_per_limb(c) + mults * N), polys * (2.0 + n_add) * N * 8);
+        work_add(c, B200HE_KERN_MODDOWN, 0, 0, polys * (D.rp2 ? 2.0 : 1.0) * N * 8);
+    }
 }
 static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_t src_outer, size_t dst_outer, int L, int mod_base)
 {
@@ -747,6 +818,8 @@ static int ntt_fwd(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_
     // unsplit limbs, more than one wave: persistent CTAs with TMA prefetch
     const unsigned pctas = (c->c == 0 && persistent && nlimbs > (size_t)c->n_sm) ? (unsigned)c->n_sm : 0u;
     PROF(c, B200HE_KERN_NTT_FWD, launch_ntt_fwd(geo(c), c->T, src, dst, src_outer, dst_outer, L, mod_base, nlimbs, pctas));
+    if (c->prof)
+        for (int l = 0; l < L; l++) work_add(c, B200HE_KERN_NTT_FWD, mod_base + l, (double)nlimbs / L * bfly_per_limb(c), (double)nlimbs / L * 2.0 * c->N * 8);
     LAUNCH_CHECK();
     return 0;
 }
@@ -761,6 +834,10 @@ static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_
     for (int l = 0; l < L; l++) n_dp += c->mods[mod_base + l].dp ? 1 : 0;
     const int kind = n_dp == 0 ? KIND_INT : n_dp == L ? KIND_DP : KIND_BOTH;
     PROF(c, B200HE_KERN_NTT_INV, launch_ntt_inv(geo(c), kind, c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F, nlimbs));
+    if (c->prof)   // fused relinearize+rescale last limb: two more operand tiles and two constant multiplies per coefficient
+        for (int l = 0; l < L; l++)
+            work_add(c, B200HE_KERN_NTT_INV, mod_base + l, (double)nlimbs / L * (bfly_per_limb(c) + (F.add ? 2.0 * c->N : 0.0)),
+                     (double)nlimbs / L * (F.add ? 4.0 : 2.0) * c->N * 8);
     LAUNCH_CHECK();
     return 0;
 }
@@ -816,6 +893,7 @@ static int add_sub(b200he_ctx *c, const b200he_batch *a, const uint32_t *ai, con
     if (sub) LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_SUB>, grid, 256, 0, c->T, A);
     else LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_ADD>, grid, 256, 0, c->T, A);
     LAUNCH_CHECK();
+    if (c->prof) c->work_bytes[B200HE_KERN_ELEMENTWISE] += (double)n * smin * 3.0 * LN * 8;
     if (smax > smin) {   // the longer operand's extra polynomials pass through (negated for b in a - b)
         const b200he_batch *big = a->size > b->size ? a : b;
         if (sub && big == b) return fail("sub: size(b) > size(a) is not supported");
@@ -859,6 +937,7 @@ extern "C" int b200he_multiply(b200he_ctx *c, const b200he_batch *a, const uint3
             A.polys = 2; A.b_polys = 2; A.L = a->L; A.mod_base = 0; A.n = n;
             LAUNCH(c, B200HE_KERN_TENSOR, k_tensor, blocks_for(n * (size_t)a->L * c->N / 2), 256, 0, c->T, A);
             LAUNCH_CHECK();
+            for (int l = 0; l < a->L && c->prof; l++) work_add(c, B200HE_KERN_TENSOR, l, n * 4.0 * 1.5 * c->N, n * 7.0 * c->N * 8);
         }
     } else {
         if (a->ntt) return fail("multiply: BFV operands must be in coefficient form");
@@ -867,6 +946,49 @@ extern "C" int b200he_multiply(b200he_ctx *c, const b200he_batch *a, const uint3
         if (n) TRY(bfv_multiply(c, a, da.d, b, db.d, n, ob.ptr()));
     }
     ob.commit();
+    return 0;
+}
+
+// MatMult CipherBatchAxis inner loop: out[i][j] = sum_k a[i][k] (x) bt[j][k], size-3 results (kernels_ew.cuh k_tensor_mac)
+extern "C" int b200he_matmul_accumulate(b200he_ctx *c, const b200he_batch *a, const b200he_batch *b, uint64_t rows, uint64_t inner, uint64_t cols,
+                                        b200he_batch *out)
+{
+    TRY(check_pair(c, a, b, out, "matmul_accumulate"));
+    if (c->scheme != B200HE_CKKS || !a->ntt) return fail("matmul_accumulate: CKKS operands in NTT form only (the BFV workload relinearizes every product)");
+    if (a->size != 2 || b->size != 2) return fail("matmul_accumulate: operands must have size 2 (got %d, %d)", a->size, b->size);
+    if (out == a || out == b) return fail("matmul_accumulate: out must not alias an input");
+    if (inner == 0) return fail("matmul_accumulate: inner dimension is 0");
+    if (rows * inner != a->count || inner * cols != b->count)
+        return fail("matmul_accumulate: a holds %llu ciphertexts (want %llu x %llu), b holds %llu (want %llu x %llu)", (unsigned long long)a->count,
+                    (unsigned long long)rows, (unsigned long long)inner, (unsigned long long)b->count, (unsigned long long)inner, (unsigned long long)cols);
+    if (rows * cols >= (uint64_t(1) << 31)) return fail("matmul_accumulate: too many result cells");
+    CK(cudaSetDevice(c->device));
+    TRY(batch_shape(out, rows * cols, 3, a->L, 1, a->scale * b->scale));
+    if (!rows || !cols) return 0;
+    const size_t LN = (size_t)a->L * c->N;
+    MacArgs A{};
+    A.a = a->d; A.b = b->d; A.out = out->d;
+    A.a_stride = a->ct_words(); A.b_stride = b->ct_words(); A.out_stride = 3 * LN;
+    A.L = a->L; A.rows = (u32)rows; A.inner = (u32)inner; A.cols = (u32)cols;
+    // a term adds two products below q^2 to the middle accumulator: runs of floor(2^127 / q^2) terms fit 128 bits
+    u64 run = ~u64(0);
+    for (int l = 0; l < a->L; l++) {
+        const hm::u128 q2 = (hm::u128)c->mods[l].q * c->mods[l].q;
+        const u64 r = (u64)((((hm::u128)1) << 127) / q2);
+        if (r < run) run = r;
+    }
+    A.reduce_every = (u32)(run < 1 ? 1 : run > 0x7fffffff ? 0x7fffffff : run);
+    constexpr int TI = 2, TJ = 2;
+    const u64 ti = (rows + TI - 1) / TI, tj = (cols + TJ - 1) / TJ, cblocks = (LN + 255) / 256;
+    if (ti * tj * cblocks >= (u64(1) << 31)) return fail("matmul_accumulate: grid too large");
+    A.tiles_j = (u32)tj;
+    A.ntiles = (u32)(ti * tj);
+    LAUNCH(c, B200HE_KERN_TENSOR_MAC, (k_tensor_mac<TI, TJ>), (unsigned)(ti * tj * cblocks), 256, 0, c->T, A);
+    LAUNCH_CHECK();
+    if (c->prof) {   // 4 wide multiply-accumulates per coefficient and term on the integer pipe; every operand read once, results written once
+        c->work_int[B200HE_KERN_TENSOR_MAC] += (double)rows * cols * inner * 4.0 * 0.5 * LN;
+        c->work_bytes[B200HE_KERN_TENSOR_MAC] += ((double)(rows + cols) * inner * 2.0 + (double)rows * cols * 3.0) * LN * 8;
+    }
     return 0;
 }
 
@@ -898,6 +1020,7 @@ static int plain_op(b200he_ctx *c, const b200he_batch *ct, const b200he_batch *p
         if (mul) LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_MUL>, grid, 256, 0, c->T, A);
         else LAUNCH(c, B200HE_KERN_ELEMENTWISE, k_ew<EW_ADD>, grid, 256, 0, c->T, A);
         LAUNCH_CHECK();
+        if (c->prof) c->work_bytes[B200HE_KERN_ELEMENTWISE] += (double)n * (mul ? 3.0 * ct->size : 2.0 * ct->size + 1.0) * ct->L * c->N * 8;
     }
     ob.commit();
     return 0;
@@ -920,6 +1043,7 @@ static int copy_limbs(b200he_ctx *c, const u64 *src, size_t src_stride, u64 *dst
     C.polys = polys; C.L_in = L_in; C.L_out = L_out; C.n = n;
     LAUNCH(c, B200HE_KERN_COPY, k_copy_limbs, blocks_for(n * polys * (size_t)L_out * c->N / 2), 256, 0, c->T, C);
     LAUNCH_CHECK();
+    if (c->prof) c->work_bytes[B200HE_KERN_COPY] += (double)n * polys * 2.0 * L_out * c->N * 8;
     return 0;
 }
 
@@ -963,12 +1087,21 @@ extern "C" int b200he_gather(b200he_ctx *c, const b200he_batch *in, const uint32
 // 2 + 2(L-1) transforms where the two separate calls need 2L + 2 + 2(L-1): every step is exact arithmetic in Z_q and
 // the transform is linear, so the last limb's mod-down correction is applied in coefficient form (InvFuse) and the two
 // corrections of each remaining limb share one transform (PreTwo).
+//
+// gal (CKKS): the Galois automorphism g of apply_galois_inplace fused into the switch -- `target` is the
+// un-permuted c1 and the kernels gather g(c1) on load; out[b] additionally receives (g(gal_src[b]), 0), gal_src = c0.
+struct GalFuse {
+    const b200he_ctx::GalTab *tab;
+    const u64 *src;
+    size_t src_stride;
+};
 static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t t_stride, const u64 *key, const u64 *add0, const u64 *add1,
-                      size_t add_stride, u64 *out, size_t out_stride, bool rescale = false)
+                      size_t add_stride, u64 *out, size_t out_stride, bool rescale = false, const GalFuse *gal = nullptr)
 {
     const size_t N = c->N, K = c->K;
     const bool ckks = c->scheme == B200HE_CKKS;
     if (rescale && (!ckks || !add0 || !add1 || L < 2)) return fail("key_switch: fused rescale needs CKKS, both addends and L >= 2");
+    if (gal && (!ckks || rescale)) return fail("key_switch: the fused Galois permutation is the NTT-form one (CKKS), without rescale");
     // scratch per ciphertext: tcoef [L][N] (CKKS), acc [2][L+1][N], rp [2][N] (+ rp2 [2][N] for the fused rescale)
     const size_t w_t = ckks ? (size_t)L * N : 0, w_acc = 2 * (size_t)(L + 1) * N, w_rp = rescale ? 4 * N : 2 * N;
     const size_t per_ct = (w_t + w_acc + w_rp) * 8;
@@ -984,15 +1117,31 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
         const u64 *tg = target + b0 * t_stride;
         KsInnerArgs A{};
         if (ckks) {
-            rc = ntt_inv(c, tg, tcoef, nb * L, t_stride, (size_t)L * N, L, 0, INV_PLAIN);
+            InvFuse G{};
+            G.gal = gal ? gal->tab->d : nullptr;
+            rc = ntt_inv(c, tg, tcoef, nb * L, t_stride, (size_t)L * N, L, 0, INV_PLAIN, gal ? &G : nullptr);
             if (rc) break;
             A.tcoef = tcoef; A.tcoef_stride = (size_t)L * N; A.target = tg; A.target_stride = t_stride;
         } else {
             A.tcoef = tg; A.tcoef_stride = t_stride; A.target = nullptr; A.target_stride = 0;
         }
         A.key = key; A.acc = acc; A.rp = rp; A.L = L; A.K = (int)K; A.B = (int)nb;
+        A.gal = gal ? gal->tab->d : nullptr;
         // (the rounded special-prime limb comes out of k_ks_inner in coefficient form: rp)
         PROF(c, B200HE_KERN_KS_INNER, launch_ks_inner(geo(c), c->T, A, nb * (L + 1)));
+        if (c->prof) {
+            // output modulus I < L: L - 1 forward transforms (CKKS: the I == J digit is reused in NTT form; BFV: L) and
+            // 2 L N multiply-accumulates; special prime: L forward + 2 inverse transforms and the same inner product.
+            // Traffic: target in coefficient and NTT form in, 2 L accumulator limbs + 2 rounded limbs out; the key once
+            // per launch (16 B per coefficient with its Shoup quotient, 8 B for FP64-domain limbs).
+            const double bf = bfly_per_limb(c), Nd = (double)N;
+            for (int I = 0; I <= L; I++) {
+                const int ki = I == L ? (int)K - 1 : I;
+                const double ntts = I == L ? L + 2.0 : (ckks ? L - 1.0 : (double)L);
+                work_add(c, B200HE_KERN_KS_INNER, ki, nb * (ntts * bf + 2.0 * L * Nd), 2.0 * L * (c->mods[ki].dp ? 1.0 : 2.0) * Nd * 8);
+            }
+            work_add(c, B200HE_KERN_KS_INNER, 0, 0, nb * (2.0 * L + 2.0 * (L + 1)) * Nd * 8);
+        }
         if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: k_ks_inner launch failed"); break; }
         ModDownArgs D{};
         D.rp = rp; D.base = acc; D.base_ct_stride = w_acc; D.base_poly_stride = (size_t)(L + 1) * N;
@@ -1001,6 +1150,10 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
         D.add_ct_stride = add_stride;
         D.out = out + b0 * out_stride; D.out_ct_stride = out_stride; D.out_poly_stride = (size_t)L * N;
         D.P = 2; D.nJ = L; D.x = (int)K - 1;
+        if (gal) {
+            D.gal = gal->tab->d; D.gal_src = gal->src + b0 * gal->src_stride; D.gal_ct_stride = gal->src_stride;
+            memcpy(D.gal_chunk, gal->tab->chunk, sizeof D.gal_chunk);
+        }
         if (rescale) {
             // last data limb: rp2 = iNTT(acc * s + addend) - u1 * s + q/2   (rounded last limb of the switched ciphertext)
             u64 *rp2 = rp + nb * 2 * N;
@@ -1091,18 +1244,27 @@ static int apply_galois_impl(b200he_ctx *c, const b200he_batch *in, uint32_t elt
     TRY(ob.shape(in->count, 2, in->L, in->ntt, in->scale));
     const size_t B = in->count, LN = (size_t)in->L * c->N;
     if (!B) { ob.commit(); return 0; }
+    if (ckks) {
+        // NTT form: no permutation pass.  The inverse transform of the target, the I == J term of the inner product and the
+        // addend of the mod-down gather through the element's table; c0 / c1 of the input ride along as plain addends for
+        // the rotate-and-add of accumulate (out = in + apply_galois(in)).
+        const b200he_ctx::GalTab *tab = nullptr;
+        TRY(galois_table(c, elt, &tab));
+        GalFuse G{ tab, in->d, 2 * LN };
+        TRY(key_switch(c, in->L, B, in->d + LN, 2 * LN, kit->second, add_input ? in->d : nullptr, add_input ? in->d + LN : nullptr, 2 * LN, ob.ptr(),
+                       2 * LN, false, &G));
+        ob.commit();
+        return 0;
+    }
+    // BFV: coefficient-form automorphism (signed index map) into out / a scratch target, then the key switch
     u64 *g1 = (u64 *)c->pool.get(B * LN * 8);
     if (!g1) return fail("apply_galois: out of device memory");
     GaloisArgs G{};
     G.src = in->d; G.dst0 = ob.ptr(); G.dst1 = g1; G.src_stride = 2 * LN; G.dst_stride = 2 * LN;
     G.elt = elt; G.L = in->L; G.logn = c->logn; G.B = B; G.add_input = add_input ? 1 : 0;
+    LAUNCH(c, B200HE_KERN_GALOIS, k_galois_coeff, blocks_for(B * 2 * LN), 256, 0, c->T, G);
     int rc = 0;
-    if (ckks) {
-        rc = galois_table(c, elt, &G.table);
-        if (!rc) LAUNCH(c, B200HE_KERN_GALOIS, k_galois_ntt, blocks_for(B * 2 * LN), 256, 0, c->T, G);
-    } else
-        LAUNCH(c, B200HE_KERN_GALOIS, k_galois_coeff, blocks_for(B * 2 * LN), 256, 0, c->T, G);
-    if (!rc && cudaGetLastError() != cudaSuccess) rc = fail("apply_galois: launch failed");
+    if (cudaGetLastError() != cudaSuccess) rc = fail("apply_galois: launch failed");
     if (!rc) {
         if (add_input) rc = key_switch(c, in->L, B, g1, LN, kit->second, ob.ptr(), in->d + LN, 2 * LN, ob.ptr(), 2 * LN);
         else rc = key_switch(c, in->L, B, g1, LN, kit->second, ob.ptr(), nullptr, 2 * LN, ob.ptr(), 2 * LN);
@@ -1348,7 +1510,18 @@ extern "C" int b200he_profile_begin(b200he_ctx *c)
     CK(cudaStreamSynchronize(c->stream));
     for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     c->recs.clear();
+    for (int i = 0; i < B200HE_KERN_COUNT; i++) c->work_int[i] = c->work_dp[i] = c->work_bytes[i] = 0;
     c->prof = true;
+    return 0;
+}
+extern "C" int b200he_profile_work(const b200he_ctx *c, double *bfly_int, double *bfly_fp64, double *bytes)
+{
+    if (!c || !bfly_int || !bfly_fp64 || !bytes) return fail("profile_work: NULL argument");
+    for (int i = 0; i < B200HE_KERN_COUNT; i++) {
+        bfly_int[i] = c->work_int[i];
+        bfly_fp64[i] = c->work_dp[i];
+        bytes[i] = c->work_bytes[i];
+    }
     return 0;
 }
 extern "C" int b200he_profile_end(b200he_ctx *c, double *ms, uint64_t *launches)
@@ -1371,7 +1544,7 @@ extern "C" int b200he_profile_end(b200he_ctx *c, double *ms, uint64_t *launches)
 }
 extern "C" const char *b200he_kernel_name(int k)
 {
-    static const char *names[B200HE_KERN_COUNT] = { "k_ntt_fwd", "k_ntt_inv", "k_ntt_inv_tail", "k_ks_inner", "k_moddown",
+    static const char *names[B200HE_KERN_COUNT] = { "k_ntt_fwd", "k_ntt_inv", "k_tensor_mac", "k_ks_inner", "k_moddown",
                                                     "k_ew", "k_tensor", "k_galois", "k_copy_limbs", "k_behz" };
     return (k >= 0 && k < B200HE_KERN_COUNT) ? names[k] : "?";
 }

@@ -132,31 +132,124 @@ __global__ void __launch_bounds__(256) k_tensor(Tables T, EwArgs A)
     st2(o + 2 * LN, mul_mod(a1.x, b1.x, m), mul_mod(a1.y, b1.y, m));
 }
 
+// Matrix of ciphertexts times matrix of ciphertexts, the inner loop of MatMult CipherBatchAxis
+// (R/src/benchmarks/ckks/seal_ckks_matmult_cipherbatchaxis_benchmark.cpp:385-422): for every output cell (i, j)
+//     out[i][j] = sum_k a[i][k] (x) b[k][j]          ((x) = the 2 x 2 -> 3 tensor product of k_tensor, size-3 result)
+// (b is held by columns: bt[j][k] = b[k][j], so both operands of a cell are contiguous runs of `inner` ciphertexts)
+// which the reference evaluates as `inner` multiply() calls and inner - 1 add_inplace() calls per cell.  Modular
+// arithmetic is exact, so summing the 128-bit products and reducing once gives the same canonical residues.
+//
+// One thread owns ONE coefficient of a TI x TJ tile of cells: the three accumulators of every cell are 128-bit integers
+// in registers (a term adds less than 2 q^2, MacArgs::reduce_every bounds the run), a step of the k loop loads
+// 2 TI + 2 TJ words and feeds 4 TI TJ wide multiply-accumulates, and nothing but the final residues is written: 
+// (2 TI + 2 TJ) / (TI TJ) loaded words per product against 7 loaded + 9 stored for the multiply()/add_inplace() pair.
+// Blocks are ordered tile-fastest: the CTAs resident at any moment work on the same coefficient range of many tiles, in
+// step through k, so the slices of a[i][k] and b[k][j] they share are served from L2 and cross HBM about once.
+struct MacArgs {
+    const u64 *a, *b;      // a: ciphertexts [rows][inner] (index i * inner + k), b: by columns, [cols][inner]; size 2, NTT form
+    u64 *out;              // [rows * cols] size-3 ciphertexts
+    size_t a_stride, b_stride, out_stride;   // words per ciphertext
+    int L;
+    u32 rows, inner, cols, tiles_j, ntiles;
+    u32 reduce_every;      // fold the accumulators after this many terms (host: floor(2^127 / max q^2), at least 1)
+};
+// (hi:lo) += x * y
+__device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 x, u64 y)
+{
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\tmadc.hi.u64 %1, %2, %3, %1;" : "+l"(lo), "+l"(hi) : "l"(x), "l"(y));
+#else
+    const unsigned __int128 s = (((unsigned __int128)hi << 64) | lo) + (unsigned __int128)x * y;
+    lo = (u64)s;
+    hi = (u64)(s >> 64);
+#endif
+}
+// any 128-bit value -> canonical residue: (hi mod q) * (2^64 mod q) + (lo mod q)
+__device__ __forceinline__ u64 fold128(u64 lo, u64 hi, const Mod &m, u64 r64q) { return mad_mod(reduce64(hi, m), r64q, reduce64(lo, m), m); }
+template <int TI, int TJ> __global__ void __launch_bounds__(256) k_tensor_mac(Tables T, MacArgs A)
+{
+    const size_t N = T.N, LN = (size_t)A.L * N;
+    const u32 tile = blockIdx.x % A.ntiles, cb = blockIdx.x / A.ntiles;
+    const size_t ce = (size_t)cb * blockDim.x + threadIdx.x;   // coefficient index within [L][N]
+    if (ce >= LN) return;
+    const Mod m = T.mods[ce / N];
+    const u64 r64q = reduce64(m.nq, m);   // 2^64 mod q
+    const u32 i0 = (tile / A.tiles_j) * TI, j0 = (tile % A.tiles_j) * TJ;
+    u64 lo[TI][TJ][3], hi[TI][TJ][3];
+#pragma unroll
+    for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+        for (int tj = 0; tj < TJ; tj++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) lo[ti][tj][c] = hi[ti][tj][c] = 0;
+    // rows / columns beyond the matrix (edge tiles) repeat the last valid one; their results are not stored
+    size_t ia[TI], jb[TJ];
+#pragma unroll
+    for (int ti = 0; ti < TI; ti++) ia[ti] = (size_t)(i0 + ti < A.rows ? i0 + ti : A.rows - 1) * A.inner;
+#pragma unroll
+    for (int tj = 0; tj < TJ; tj++) jb[tj] = (size_t)(j0 + tj < A.cols ? j0 + tj : A.cols - 1) * A.inner;
+    u32 run = 0;
+    for (u32 k = 0; k < A.inner; k++) {
+        u64 a0[TI], a1[TI], b0[TJ], b1[TJ];
+#pragma unroll
+        for (int ti = 0; ti < TI; ti++) {
+            const u64 *pa = A.a + (ia[ti] + k) * A.a_stride + ce;
+            a0[ti] = ldg1(pa);
+            a1[ti] = ldg1(pa + LN);
+        }
+#pragma unroll
+        for (int tj = 0; tj < TJ; tj++) {
+            const u64 *pb = A.b + (jb[tj] + k) * A.b_stride + ce;
+            b0[tj] = ldg1(pb);
+            b1[tj] = ldg1(pb + LN);
+        }
+#pragma unroll
+        for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+            for (int tj = 0; tj < TJ; tj++) {
+                mac128(lo[ti][tj][0], hi[ti][tj][0], a0[ti], b0[tj]);
+                mac128(lo[ti][tj][1], hi[ti][tj][1], a0[ti], b1[tj]);
+                mac128(lo[ti][tj][1], hi[ti][tj][1], a1[ti], b0[tj]);
+                mac128(lo[ti][tj][2], hi[ti][tj][2], a1[ti], b1[tj]);
+            }
+        if (++run == A.reduce_every && k + 1 < A.inner) {
+            run = 0;
+#pragma unroll
+            for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+                for (int tj = 0; tj < TJ; tj++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        lo[ti][tj][c] = fold128(lo[ti][tj][c], hi[ti][tj][c], m, r64q);
+                        hi[ti][tj][c] = 0;
+                    }
+        }
+    }
+#pragma unroll
+    for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+        for (int tj = 0; tj < TJ; tj++) {
+            if (i0 + ti >= A.rows || j0 + tj >= A.cols) continue;
+            u64 *o = A.out + ((size_t)(i0 + ti) * A.cols + (j0 + tj)) * A.out_stride + ce;
+#pragma unroll
+            for (int c = 0; c < 3; c++) o[(size_t)c * LN] = fold128(lo[ti][tj][c], hi[ti][tj][c], m, r64q);
+        }
+}
+
 // ------------------------------------------------------------------------------------ K8
-// NTT-form Galois automorphism of a size-2 ciphertext batch: out0 = g(c0) -> dst ct poly 0,
-// g(c1) -> target buffer [B][L][N]; dst poly 1 is produced by the key switch that follows.
+// Coefficient-form (BFV) Galois automorphism of a size-2 ciphertext batch: out0 = g(c0) -> dst ct poly 0,
+// g(c1) -> target buffer [B][L][N]; dst poly 1 is produced by the key switch that follows.  (The NTT-form automorphism
+// of CKKS has no kernel of its own: it is a gather on load inside the key switch, kernels_ks.cuh / kernels_moddown.cuh.)
 struct GaloisArgs {
     const u64 *src;       // [B][2][L][N]
     u64 *dst0;            // g(c0): dst0 + b*dst_stride + l*N
     u64 *dst1;            // g(c1): dst1 + b*L*N + l*N
     size_t src_stride, dst_stride;
-    const u32 *table;     // [N] NTT-form permutation (CKKS)
     u32 elt;              // Galois element (BFV coefficient form)
     int L, logn;
     size_t B;
     int add_input;        // dst0 = g(c0) + c0 (rotate-and-add of accumulate: the key switch then adds c1 as its second addend)
 };
-__global__ void __launch_bounds__(256) k_galois_ntt(Tables T, GaloisArgs A)
-{
-    const size_t N = T.N, per_ct = 2 * (size_t)A.L * N;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= A.B * per_ct) return;
-    const size_t b = gid / per_ct, rem = gid % per_ct;
-    const size_t p = rem / ((size_t)A.L * N), le = rem % ((size_t)A.L * N), l = le / N, e = le % N;
-    const u64 v = A.src[b * A.src_stride + p * A.L * N + l * N + A.table[e]];
-    if (p == 0) A.dst0[b * A.dst_stride + le] = A.add_input ? add_mod(v, A.src[b * A.src_stride + le], T.mods[l].q) : v;
-    else A.dst1[b * A.L * N + le] = v;
-}
 // Coefficient-form automorphism (BFV): coefficient i moves to i*elt mod N, negated when floor(i*elt/N) is odd.
 __global__ void __launch_bounds__(256) k_galois_coeff(Tables T, GaloisArgs A)
 {

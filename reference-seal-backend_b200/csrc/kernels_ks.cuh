@@ -27,6 +27,7 @@ struct KsInnerArgs {
     u64 *acc;              // [B][2][L+1][N]
     u64 *rp;               // [B][2][N]: rounded special-prime limb in coefficient form
     int L, K, B;           // B = ciphertexts in this launch
+    const u32 *gal;        // Galois permutation of the NTT-form target, applied on load ([N], nullptr: none): see InvFuse::gal
 };
 // lazy accumulator of the inner product (either domain) -> canonical residue
 __device__ __forceinline__ u64 acc_finish(u64 a, const Mod &m) { return m.dp ? dp_canon(as_d(a), m) : reduce_full(a, m); }
@@ -69,11 +70,13 @@ __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs
         };
         if (A.target && I == J) {
             const u64 *tp = A.target + (size_t)b * A.target_stride + (size_t)J * N + off;
-            for_pairs_co(tid, [&](int reg, int e) {
-                ulonglong2 v = ldg2(tp + e);
-                x[reg] = v.x;
-                x[reg + 1] = v.y;
-            });
+            if (A.gal) gather_pairs_co(x, tp - off, A.gal + off, tid);
+            else
+                for_pairs_co(tid, [&](int reg, int e) {
+                    ulonglong2 v = ldg2(tp + e);
+                    x[reg] = v.x;
+                    x[reg + 1] = v.y;
+                });
             prefetch_key0();
             __syncthreads();   // the transform buffer may still be read by the previous digit's transform
             co_to_contig(x, sm, tid);

@@ -41,12 +41,21 @@ struct ModDownArgs {
     // ciphertext, x2 = its modulus id.  out = (base * s + addend) * r - NTT((u1 * s + u2) * r), s = q_x^{-1}, r = q_x2^{-1}
     const u64 *rp2;
     int x2;
+    // Galois automorphism fused into the addend of polynomial 0 (K8): out[b][0][j] += g(gal_src[b][j]),
+    // g(x)[i] = x[gal[i]] -- the g(c0) term of apply_galois_inplace, gathered from the INPUT ciphertext instead of
+    // being written by a permutation pass.  gal_chunk[r] = the 2^LOGN-coefficient chunk of the source limb that chunk r
+    // of the output gathers from (the table maps aligned chunks onto aligned chunks).
+    const u32 *gal;        // [N] or nullptr
+    const u64 *gal_src;    // gal_src + b*gal_ct_stride + j*N
+    size_t gal_ct_stride;
+    unsigned char gal_chunk[4];
 };
 // Shared memory: transform buffer | TMA landing zone of the accumulator tile | of the addend tile | mbarrier.
 // The two epilogue operands of a CTA are contiguous 8 NL-byte tiles; thread 0 starts their bulk copies before the
 // transform and the epilogue reads them from shared memory.
 template <int LOGN> struct ModDownCfg {
     static constexpr int SMEM_BYTES = 3 * NttCfg<LOGN>::SMEM_BYTES + 16;
+    static constexpr int SMEM_BYTES_GAL = SMEM_BYTES + 4 * (1 << LOGN);   // + this chunk of the Galois table (u32)
 };
 // DP = Mod::dp of the output limb's modulus, a compile-time constant (one branch at the top of the kernel, two complete
 // instances, as in k_ks_inner).  In the FP64 instance the lifted input, the transform, and the epilogue's two constant
@@ -81,11 +90,20 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
     // read the whole tile before it writes.
     // (thread 0 initialises, arms and uses the barrier; everyone else first touches it after the CTA-wide barriers of
     // the transform, which order the initialisation before their wait)
+    // Galois-fused addend (polynomial 0 only): the chunk of the input limb that this output chunk gathers from lands in
+    // stage_a, this chunk of the table behind the barrier word.  A contiguous addend of the same launch (rotate-and-add)
+    // shares stage_a when it is the same tile (unsplit limbs) and is read straight from global memory otherwise.
+    const bool gal = A.gal && p == 0;
+    const u32 *tab_sm = reinterpret_cast<const u32 *>(bar + 2);
+    const u64 *gp = gal ? A.gal_src + (size_t)b * A.gal_ct_stride + (size_t)j * N + (size_t)A.gal_chunk[r] * NL : nullptr;
+    const bool ap_staged = ap && (!gal || gp == ap), ap_direct = ap && !ap_staged;
     if (tid == 0) {
         tma_bar_init(bar);
-        tma_bar_expect(bar, (ap ? 2u : 1u) * NL * 8);
+        tma_bar_expect(bar, ((ap_staged || gal) ? 2u : 1u) * NL * 8 + (gal ? NL * 4u : 0u));
         tma_load_1d(stage_b, bp, NL * 8, bar);
-        if (ap) tma_load_1d(stage_a, ap, NL * 8, bar);
+        if (ap_staged) tma_load_1d(stage_a, ap, NL * 8, bar);
+        else if (gal) tma_load_1d(stage_a, gp, NL * 8, bar);
+        if (gal) tma_load_1d(const_cast<u32 *>(tab_sm), A.gal + off, NL * 4, bar);
     }
     if constexpr (DP) {
         const double wq30 = 1073741824.0 * m.dqinv, nq = m.dnq;
@@ -120,9 +138,14 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
             const ulonglong2 bv = ld2(stage_b + e);
             double v0 = dp_mul(__dadd_rn(dp_from(bv.x), -as_d(x[reg])), sd, sq, nq), v1 = dp_mul(__dadd_rn(dp_from(bv.y), -as_d(x[reg + 1])), sd, sq, nq);
             if (ap) {
-                const ulonglong2 av = ld2(stage_a + e);
+                const ulonglong2 av = ap_direct ? ldg2(ap + e) : ld2(stage_a + e);
                 v0 = __dadd_rn(v0, dp_from(av.x));
                 v1 = __dadd_rn(v1, dp_from(av.y));
+            }
+            if (gal) {   // + g(c0): gathered from the staged source chunk
+                const u32 t0 = tab_sm[e] & (NL - 1), t1 = tab_sm[e + 1] & (NL - 1);
+                v0 = __dadd_rn(v0, dp_from(stage_a[t0]));
+                v1 = __dadd_rn(v1, dp_from(stage_a[t1]));
             }
             st2(op + e, dp_canon(v0, m), dp_canon(v1, m));
         });
@@ -163,9 +186,14 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
         u64 v0 = shoup(sub_mod(bv.x, u0, m.q), qi.x, qi.y, m.q);
         u64 v1 = shoup(sub_mod(bv.y, u1, m.q), qi.x, qi.y, m.q);
         if (ap) {
-            ulonglong2 av = ld2(stage_a + e);
+            const ulonglong2 av = ap_direct ? ldg2(ap + e) : ld2(stage_a + e);
             v0 = add_mod(v0, av.x, m.q);
             v1 = add_mod(v1, av.y, m.q);
+        }
+        if (gal) {   // + g(c0): gathered from the staged source chunk
+            const u32 t0 = tab_sm[e] & (NL - 1), t1 = tab_sm[e + 1] & (NL - 1);
+            v0 = add_mod(v0, stage_a[t0], m.q);
+            v1 = add_mod(v1, stage_a[t1], m.q);
         }
         st2(op + e, v0, v1);
     });

@@ -112,6 +112,9 @@ struct InvFuse {
     size_t add_ct_stride, add_poly_stride;
     const u64 *sub;        // [nlimbs][N] coefficient form (the rounded special-prime limb)
     int P, x;              // polys per ciphertext; x = modulus id of the prime dropped by the key switch
+    // Galois automorphism applied on load (plain transform only): dst = iNTT(g(src)), g(src)[i] = src[gal[i]] -- the
+    // target of a rotation's key switch enters the key switch without a permutation pass
+    const u32 *gal;        // [N] or nullptr
 };
 __device__ __forceinline__ u64 inv_post(u64 v /* finished, canonical */, u64 subv, const Mod &m, ulonglong2 s, u64 fix)
 {
@@ -184,6 +187,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
             x[reg] = add_mod(shoup(v.x, fs.x, fs.y, m.q), a.x, m.q);
             x[reg + 1] = add_mod(shoup(v.y, fs.x, fs.y, m.q), a.y, m.q);
         });
+    } else if (F.gal) {
+        gather_pairs_co(x, in - (size_t)r * NL, F.gal + (size_t)r * NL, tid);
     } else {
         for_pairs_co(tid, [&](int reg, int e) {
             ulonglong2 v = ldg2(in + e);

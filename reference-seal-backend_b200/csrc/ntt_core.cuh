@@ -560,6 +560,41 @@ __device__ __forceinline__ ulonglong2 ldg2(const u64 *p)
 #endif
 }
 __device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+// ---- Galois permutation applied on load (K8 fused into the key switch) ----
+// NTT-form automorphism: g(x)[i] = x[table[i]] (SEAL GaloisTool::apply_galois_ntt).  The table maps every aligned block of
+// 2^k consecutive indices onto an aligned block of 2^k indices (consecutive i differ in the top bits of brv(i)), so a
+// warp that gathers the 64 coefficients of one lane-interleaved access reads one contiguous 512-byte range of the
+// source, lanes permuted: the gather costs no extra sectors.
+struct TabPair { u32 a, b; };
+__device__ __forceinline__ TabPair ld_tab2(const u32 *p)   // table entries p[0], p[1] (p 8-byte aligned)
+{
+#if defined(__CUDA_ARCH__)
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    return TabPair{ t.x, t.y };
+#else
+    return TabPair{ p[0], p[1] };
+#endif
+}
+__device__ __forceinline__ u64 ldg1(const u64 *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// x <- limb[table[.]] in the lane-interleaved layout of chunk `off`: all table loads are issued before the first data load
+__device__ __forceinline__ void gather_pairs_co(u64 (&x)[16], const u64 *__restrict__ limb, const u32 *__restrict__ tab_chunk, int tid)
+{
+    TabPair t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = ld_tab2(tab_chunk + co_elem(tid, i));
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        x[2 * i] = ldg1(limb + t[i].a);
+        x[2 * i + 1] = ldg1(limb + t[i].b);
+    }
+}
 __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
 
 }   // namespace b200he

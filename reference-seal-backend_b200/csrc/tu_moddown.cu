@@ -8,20 +8,20 @@ void launch_moddown_kind(const Geo &g, int kind, const Tables &T, const ModDownA
 {
     const unsigned grid = (unsigned)(units << g.c);
     if (kind == KIND_INT) {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, D));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, 1u << g.c, T, D));
     } else if (kind == KIND_DP) {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_dp<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, D));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_dp<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, 1u << g.c, T, D));
     } else {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_mix<LG, CC>), grid, NttCfg<LG>::THREADS, ModDownCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, D));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_mix<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, 1u << g.c, T, D));
     }
 }
 
 template <int LG, int CC> static int attrs()
 {
 #ifndef B200HE_EMU
-    cudaError_t e = cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_moddown_dp<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_moddown_mix<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_moddown<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES_GAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_moddown_dp<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES_GAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_moddown_mix<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModDownCfg<LG>::SMEM_BYTES_GAL);
     return (int)e;
 #else
     return 0;

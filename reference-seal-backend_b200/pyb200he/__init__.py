@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200he_batch_download_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_batch_upload_scattered": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_batch_download_scattered": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b200he_batch_copy_from": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200he_batch_count": (C.c_uint64, [C.c_void_p]),
     "b200he_batch_size": (C.c_int, [C.c_void_p]),
     "b200he_batch_level": (C.c_int, [C.c_void_p]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "b200he_add": (C.c_int, [C.c_void_p, C.c_void_p, u32p, C.c_void_p, u32p, C.c_uint64, C.c_void_p]),
     "b200he_sub": (C.c_int, [C.c_void_p, C.c_void_p, u32p, C.c_void_p, u32p, C.c_uint64, C.c_void_p]),
     "b200he_multiply": (C.c_int, [C.c_void_p, C.c_void_p, u32p, C.c_void_p, u32p, C.c_uint64, C.c_void_p]),
+    "b200he_matmul_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200he_relinearize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200he_rotate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200he_rotate_columns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -67,6 +69,7 @@ SIGNATURES = {
     "b200he_launch_count": (C.c_uint64, [C.c_void_p]),
     "b200he_profile_begin": (C.c_int, [C.c_void_p]),
     "b200he_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), u64p]),
+    "b200he_profile_work": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200he_kernel_name": (C.c_char_p, [C.c_int]),
 }
 
@@ -149,6 +152,11 @@ class Batch:
         assert a.size % words == 0, (a.size, words)
         self.ctx._ck(self.lib.b200he_batch_upload(self.h, first, a.size // words, a.ctypes.data))
         self.ctx.sync()   # the host array may be a temporary
+        return self
+
+    def copy_from(self, other):
+        """this batch = a copy of a batch of another context / GPU (device to device, stream-ordered)"""
+        self.ctx._ck(self.lib.b200he_batch_copy_from(self.h, other.h))
         return self
 
     def upload_from(self, ptr, first, n):
@@ -271,6 +279,13 @@ class Context:
     def multiply(self, a, b, ai=None, bi=None, n=None, out=None):
         return self._binary(self.lib.b200he_multiply, a, b, ai, bi, n, out)
 
+    def matmul_accumulate(self, a, b, rows, inner, cols, out=None):
+        """out[i * cols + j] = sum_k a[i * inner + k] (x) b[j * inner + k] (size 3; b holds the right-hand matrix by columns):
+        MatMult CipherBatchAxis' inner loop"""
+        out = out or Batch(self)
+        self._ck(self.lib.b200he_matmul_accumulate(self.h, a.h, b.h, rows, inner, cols, out.h))
+        return out
+
     def _unary(self, fn, a, out, *args):
         out = out or Batch(self)
         self._ck(fn(self.h, a.h, *args, out.h))
@@ -348,3 +363,10 @@ class Context:
         n = (C.c_uint64 * KERNEL_CLASSES)()
         self._ck(self.lib.b200he_profile_end(self.h, ms, n))
         return {self.lib.b200he_kernel_name(i).decode(): (ms[i], int(n[i])) for i in range(KERNEL_CLASSES) if n[i]}
+
+    def profile_work(self):
+        """algorithmic work of the launches of the last profile: {kernel class: (integer-pipe butterfly equivalents,
+        FP64-pipe butterfly equivalents, HBM bytes)}"""
+        bi, bd, by = ((C.c_double * KERNEL_CLASSES)() for _ in range(3))
+        self._ck(self.lib.b200he_profile_work(self.h, bi, bd, by))
+        return {self.lib.b200he_kernel_name(i).decode(): (bi[i], bd[i], by[i]) for i in range(KERNEL_CLASSES) if bi[i] or bd[i] or by[i]}

@@ -1,6 +1,8 @@
 // cuda_shim.cpp -- fiber scheduler behind tests/emu/cuda_shim.h (TEST INFRASTRUCTURE).
 #include "cuda_shim.h"
 
+#include <mutex>
+
 #include <stdio.h>
 #include <sys/mman.h>
 
@@ -40,8 +42,12 @@ void sync() { swapcontext(&g_fibers[g_cur].ctx, &g_main); }
 void cluster_sync() { sync(); }
 
 // the `cluster` consecutive blocks of a thread-block cluster run together (their fibers share one scheduler round)
+// one grid at a time: the fiber scheduler and the emulated thread indices are process-wide, while the backend issues work
+// for every "GPU" from its own host thread
+static std::mutex g_grid_mtx;
 void run_grid(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body, unsigned cluster)
 {
+    std::lock_guard<std::mutex> lock(g_grid_mtx);
     g_body = &body;
     gridDim.x = grid;
     blockDim.x = block;

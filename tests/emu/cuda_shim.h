@@ -59,6 +59,10 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 template <class T> static inline cudaError_t cudaFuncSetAttribute(T, int, int) { return 0; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return 0; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = nullptr; return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int, const void *s, int, size_t n, cudaStream_t) { memmove(d, s, n); return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }

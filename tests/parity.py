@@ -112,6 +112,19 @@ def case_scattered(env, n=7):
     assert b.download_scattered(0, 0) == []
 
 
+def case_copy_between_contexts(env, n=3):
+    """b200he_batch_copy_from: the cross-GPU exchange step of logistic regression (partial collapse sums meet on GPU 0),
+    here between two contexts of the same device"""
+    other = hb.Context(env.scheme, env.N, env.moduli, env.orc.psi(), env.t, lib=env.ctx.lib)
+    x = env.rand_ct(n)
+    src = other.batch(x, size=2, L=env.Ltop, scale=3.0)
+    dst = hb.Batch(env.ctx).copy_from(src)
+    assert (dst.count, dst.size, dst.L, dst.scale) == (n, 2, env.Ltop, 3.0)
+    eq(dst.download(), x, "copy between contexts")
+    eq(env.ctx.add(dst, dst).download()[1], env.orc.add(env.Ltop, 2, x[1].reshape(-1), x[1].reshape(-1)), "the copy is usable on the destination stream")
+    other.close()
+
+
 def case_extremes(env):
     """Worst-case magnitudes for the lazy-reduction schedules of both arithmetic domains (integer pipe, and the FP64
     domain of primes below 2^46): every residue q-1, every residue 0, alternating q-1 / 0 and q-1 / 1 patterns, with
@@ -189,6 +202,37 @@ def case_elementwise(env, n0=3, n1=2):
     c3, d3 = env.rand_ct(2, size=3), env.rand_ct(2, size=3)
     got = env.ctx.add(env.batch(c3, size=3), env.batch(d3, size=3)).download()
     eq(got[1], env.orc.add(L, 3, c3[1].reshape(-1), d3[1].reshape(-1)), "add size 3")
+
+
+def case_matmul_accumulate(env, rows=3, inner=5, cols=3, L=None):
+    """MatMult CipherBatchAxis inner loop (R/src/benchmarks/ckks/seal_ckks_matmult_cipherbatchaxis_benchmark.cpp:385-422):
+    out[i][j] = sum_k a[i][k] (x) b[k][j] in one pass == the reference's multiply / add_inplace sequence (b is passed by
+    columns: bt[j][k]); odd shapes exercise the edge tiles"""
+    L = env.Ltop if L is None else L
+    a, b = env.rand_ct(rows * inner, L=L), env.rand_ct(inner * cols, L=L)
+    A, B = env.batch(a, L=L, scale=2.0 ** 30), env.batch(b, L=L, scale=2.0 ** 30)
+    out = env.ctx.matmul_accumulate(A, B, rows, inner, cols)
+    assert out.size == 3 and out.count == rows * cols and out.L == L and out.scale == 2.0 ** 60
+    got = out.download()
+    for i in range(rows):
+        for j in range(cols):
+            want = None
+            for k in range(inner):
+                t = env.orc.ckks_multiply(L, a[i * inner + k].reshape(-1), b[j * inner + k].reshape(-1))
+                want = t if want is None else env.orc.add(L, 3, want, t)
+            eq(got[i * cols + j], want, f"matmul_accumulate cell ({i},{j})")
+    # worst-case magnitudes: every residue q - 1, more terms than one accumulator run holds for 60-bit primes
+    n = 140
+    ones = np.empty((1, 2, L, env.N), dtype=np.uint64)
+    for l in range(L):
+        ones[:, :, l, :] = env.moduli[l] - np.uint64(1)
+    x = np.ascontiguousarray(np.repeat(ones, n, axis=0))
+    got = env.ctx.matmul_accumulate(env.batch(x, L=L), env.batch(x, L=L), 1, n, 1).download()
+    t = env.orc.ckks_multiply(L, ones.reshape(-1), ones.reshape(-1)).reshape(3, L, env.N)
+    want = np.empty_like(t)
+    for l in range(L):
+        want[:, l, :] = (t[:, l, :].astype(object) * n % int(env.moduli[l])).astype(np.uint64)
+    eq(got[0], want, "matmul_accumulate, all residues q - 1, 140 terms")
 
 
 def case_relinearize(env, n=2, L=None):

@@ -46,6 +46,14 @@ def test_elementwise(ckks):
     parity.case_elementwise(ckks)
 
 
+def test_copy_between_contexts(ckks):
+    parity.case_copy_between_contexts(ckks)
+
+
+def test_matmul_accumulate(ckks):
+    parity.case_matmul_accumulate(ckks)
+
+
 def test_relinearize(ckks):
     for L in range(ckks.Ltop, 0, -1):
         parity.case_relinearize(ckks, L=L)
@@ -119,6 +127,8 @@ def test_split_limb(emu_lib):
         parity.case_relinearize(env, n=1)
         parity.case_rescale(env, n=1, sizes=(2,))
         parity.case_relin_rescale_fused(env, n=1)
+        parity.case_rotate(env, n=1, steps=(1,))      # Galois gather across chunks (key switch fused permutation)
+        parity.case_dot(env, n0=1, n1=1, count=2)     # rotate-and-add: contiguous addend + gathered addend
         env.close()
     env = parity.Env(emu_lib, CKKS, 16384, [46, 47, 46, 60], galois_steps=(1,))
     parity.case_extremes(env)

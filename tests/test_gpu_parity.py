@@ -58,6 +58,16 @@ def test_elementwise(ckks):
     parity.case_elementwise(ckks)
 
 
+def test_copy_between_contexts(ckks):
+    parity.case_copy_between_contexts(ckks)
+
+
+def test_matmul_accumulate(ckks):
+    parity.case_matmul_accumulate(ckks, rows=5, inner=9, cols=4)
+    if ckks.Ltop > 2:
+        parity.case_matmul_accumulate(ckks, rows=2, inner=3, cols=2, L=ckks.Ltop - 1)
+
+
 def test_relinearize(ckks):
     for L in sorted({ckks.Ltop, max(1, ckks.Ltop - 1), 1}, reverse=True):
         parity.case_relinearize(ckks, L=L)

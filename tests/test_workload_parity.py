@@ -42,8 +42,13 @@ def read_trace(d, tag):
     return data.reshape(count, size, L, N), struct.unpack("<d", struct.pack("<Q", scale_bits))[0], total
 
 
+GPUS = [None]   # HEB_B200_GPUS of the harness runs (None: the environment's / one GPU)
+
+
 def run_harness(plugin, args, trace_dir, picks=None, timeout=1500):
     env = dict(os.environ, HEB_B200_TRACE_DIR=str(trace_dir), HEB_B200_SEED=str(SEED))
+    if GPUS[0]:
+        env["HEB_B200_GPUS"] = str(GPUS[0])
     for tag, ids in (picks or {}).items():
         env["HEB_B200_TRACE_PICK_" + tag] = ",".join(str(i) for i in ids)
     p = subprocess.run([HARNESS, "--backend_lib_path", plugin, "--iterations", "1"] + args, capture_output=True, text=True, env=env, timeout=timeout)
@@ -181,6 +186,25 @@ def test_emu_matmul_workloads(emu_plugin, tmp_path, scheme):
 
 def test_emu_logreg_workload(emu_plugin, tmp_path):
     check_logreg(emu_plugin, tmp_path, 2048, 6, 3, batch=5, n_features=6)
+
+
+def test_emu_result_space_partitioning(emu_plugin, tmp_path):
+    """with several GPUs (here: several contexts of the emulation) the result space is partitioned -- the longer
+    operand split in blocks, the other replicated; matrix rows or columns; logistic-regression samples with the partial
+    collapse sums exchanged device to device -- and store() still returns the reference's bits in the reference's order"""
+    GPUS[0] = 3
+    try:
+        check_vector(emu_plugin, tmp_path, CKKS, "mul", 2048, 2, 45, 45, n=16, s0=4, s1=2)    # parameter 0 split
+        check_vector(emu_plugin, tmp_path, CKKS, "dot", 2048, 2, 40, 40, n=10, s0=2, s1=5)    # parameter 1 split: results interleave
+        check_vector(emu_plugin, tmp_path, BFV, "dot", 2048, 2, 45, 20, n=9, s0=1, s1=2)      # fewer samples than GPUs
+        check_matmul(emu_plugin, tmp_path, CKKS, 0, 2048, 2, 45, 45, dims=(2, 5, 4))          # Val, columns of M1 split
+        check_matmul(emu_plugin, tmp_path, CKKS, 1, 2048, 3, 45, 45, dims=(4, 3, 2))          # CipherBatchAxis, rows of M0 split
+        check_matmul(emu_plugin, tmp_path, CKKS, 1, 2048, 3, 45, 45, dims=(2, 3, 5))          # CipherBatchAxis, columns of M1 split
+        check_matmul(emu_plugin, tmp_path, BFV, 1, 2048, 3, 40, 20, dims=(2, 3, 4))
+        check_matmul(emu_plugin, tmp_path, CKKS, 2, 2048, 3, 45, 45, dims=(4, 4, 2))          # Row
+        check_logreg(emu_plugin, tmp_path, 2048, 6, 3, batch=7, n_features=6)
+    finally:
+        GPUS[0] = None
 
 
 # ------------------------------------------------------------------------------------------- GPU: the real plugin
