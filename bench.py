@@ -305,7 +305,6 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ranks = Ranks(dist, device=torch.device("cuda", local))
 
@@ -402,10 +401,27 @@ def run_b200(args):
             step()
         ev1.record(stream)
         prof = ctx.profile_end()
+        work = ctx.profile_work()
         barrier()
     launches = ctx.launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = clk.summary()
+
+    # ---- sustained leg: the same step back to back for >= args.sustain seconds (clocks and power under a long load)
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(int(args.sustain * 1.1 / (ms_total / args.steps / 1e3)), args.steps)
+        barrier()
+        with ClockSampler(local, period=0.01) as clk_s:
+            ev0.record(stream)
+            for _ in range(n_sus):
+                step()
+            ev1.record(stream)
+            ctx.sync()
+            barrier()
+        sus_ms = max_over_ranks(ev0.elapsed_time(ev1))
+        sustained = {"seconds": sus_ms / 1e3, "steps": n_sus, "ms_per_step": sus_ms / n_sus, "value": BATCH * world * n_sus / (sus_ms / 1e3),
+                     "unit": UNIT, "clocks": clk_s.summary()}
 
     # ---- end to end through the C ABI with host buffers (pinned): H2D + compute + D2H per step.  Several streams
     # are involved, so the region is bracketed by events on the default stream that every stream joins.
@@ -466,7 +482,10 @@ def run_b200(args):
     got = out_pins[(args.steps - 1) % 2].numpy()[:words_out].view(np.uint64)
     assert np.array_equal(got, chk.download().reshape(-1)), "timed path result differs from a fresh evaluation"
 
+    names = select_configs(args.configs, world)
     if rank != 0:
+        if names:
+            ranks.barrier()   # rank 0 drives the plugin's own multi-GPU path over all the GPUs meanwhile
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -477,22 +496,21 @@ def run_b200(args):
     top = max(prof.items(), key=lambda kv: kv[1][0])
     top_name, (top_ms, top_n) = top
     dp = [1 if int(q).bit_length() <= DP_MAX_BITS and not os.environ.get("B200HE_NO_DP") else 0 for q in host.moduli]
-    alg = algorithmic_bytes(top_name, BATCH, L, K, N, dp)
-    achieved = alg / (top_ms / top_n / 1e3) / 1e9 if alg else None
+    bf_int_peak, bf_dp_peak, bf_src = butterfly_peak()
+    # per kernel class, from the library's own work accounting of the timed launches (b200he_profile_work)
+    kr = kernel_rooflines(prof, work, args.steps, peak, bf_int_peak, bf_dp_peak)
+    top_r = kr[top_name]
+    achieved = top_r["hbm_GBps"]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(top_name)
-    ntt_limbs = {"k_ks_inner": L * L + 2, "k_moddown": 2 * (L - 1), "k_ntt_inv": (L + 2) / 2.0}.get(top_name, 0) * BATCH
-    bfe = butterfly_equivalents(top_name, BATCH, L, K, N, dp)
-    bf_int_peak, bf_dp_peak, bf_src = butterfly_peak()
-    # compute floor of the launch: each butterfly on its pipe at that pipe's measured register-resident rate
-    bf_rate = bf_peak = None
-    if bfe:
-        floor_s = bfe[0] / bf_int_peak + bfe[1] / bf_dp_peak
-        bf_rate = (bfe[0] + bfe[1]) / (top_ms / top_n / 1e3)
-        bf_peak = (bfe[0] + bfe[1]) / floor_s
+    bf_rate = top_r["butterflies_per_s"]
+    bf_peak = bf_rate / top_r["pipe_frac"] if bf_rate and top_r["pipe_frac"] else None
+    # the whole step against its floors: the time its butterflies need at the measured pipe rates, its bytes at the measured copy rate
+    step_pipe_floor = sum(w[0] / bf_int_peak + w[1] / bf_dp_peak for w in work.values()) / args.steps
+    step_hbm_floor = sum(w[2] for w in work.values()) / args.steps / (peak * 1e9)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -505,15 +523,20 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": top_ms / top_n, "share_of_step": top_ms / (ms_total_local(prof)),
-                     "limb_ntts_per_s": ntt_limbs / (top_ms / top_n / 1e3) if ntt_limbs else None,
+                     "algorithmic_bytes_per_launch": top_r["algorithmic_bytes_per_launch"],
                      # the NTT-bearing kernels are bound by the arithmetic pipes, not HBM: fraction of the measured
                      # register-resident butterfly rate of the chip, 60-bit limbs on the integer pipe and limbs below
                      # 2^46 on the FP64 pipe, weighted by this launch's mix
                      "int_pipe": {"achieved": bf_rate, "peak": bf_peak, "unit": "butterflies/s",
                                   "frac": (bf_rate / bf_peak) if bf_rate else None, "peak_source": bf_src,
-                                  "fp64_share_of_butterflies": (bfe[1] / (bfe[0] + bfe[1])) if bfe else None,
-                                  "int_peak": bf_int_peak, "fp64_peak": bf_dp_peak}},
+                                  "fp64_share_of_butterflies": top_r["fp64_share_of_butterflies"],
+                                  "int_peak": bf_int_peak, "fp64_peak": bf_dp_peak},
+                     "step": {"ms": ms_total / args.steps, "pipe_floor_ms": step_pipe_floor * 1e3, "hbm_floor_ms": step_hbm_floor * 1e3,
+                              "frac_of_binding_floor": max(step_pipe_floor, step_hbm_floor) * 1e3 / (ms_total / args.steps)}},
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+        "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) and kk.endswith(("frac", "ms_per_step")) else vv) for kk, vv in v.items()}
+                    for k, v in sorted(kr.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+        "sustained": sustained,
     }
     n_dp = sum(dp[:L])
     ntt_peak = L / ((L - n_dp) / bf_int_peak + n_dp / bf_dp_peak)   # the transformed limbs cycle over the L data moduli
@@ -523,9 +546,29 @@ def run_b200(args):
     ntt_metric["fwd_frac_of_hbm_peak"] = ntt_metric["fwd_GBps_algorithmic"] / peak
     line["ntt_limb_ops"] = ntt_metric   # per GPU
     line["cpu_baseline"] = cpu_baseline(budget_s=12.0) if world == 1 else None
+    # ---- every BASELINE config at its stated shape through the plugin (N > 1: the fixed-work ones, split over the N GPUs)
+    if names:
+        torch.cuda.empty_cache()   # (the harness processes allocate on the same GPUs: 180 GB leaves room for both)
+        block = run_plugin_configs(names, world, peak, bf_int_peak, bf_dp_peak, budget_s=args.configs_budget)
+        line["configs" if world == 1 else "strong_scaling"] = block
+        if dist is not None:
+            ranks.barrier()
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def select_configs(spec, world):
+    """which plugin configs this run drives: every rank evaluates the same answer"""
+    if spec == "none":
+        return []
+    if spec == "all":
+        return list(PLUGIN_CONFIGS) if world == 1 else list(STRONG_SCALING)
+    names = [x for x in spec.split(",") if x]
+    for x in names:
+        if x not in PLUGIN_CONFIGS:
+            raise SystemExit(f"--configs: unknown config {x} (known: {', '.join(PLUGIN_CONFIGS)})")
+    return names
 
 
 def ms_total_local(prof):
@@ -606,6 +649,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--configs", default="all", help="BASELINE configs driven through the plugin: all | none | C1,C2add,C2mul,C3,C4val,C4row,C4cba,C5")
+    ap.add_argument("--configs-budget", type=float, default=200.0, help="wall-clock budget of the configs block in seconds (later configs are skipped)")
+    ap.add_argument("--sustain", type=float, default=1.0, help="seconds of the sustained leg (0: skip)")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 on their own (NCCL prints its
     # version there at communicator creation) are sent to stderr; the result line goes to the real stdout

@@ -979,14 +979,14 @@ extern "C" int b200he_matmul_accumulate(b200he_ctx *c, const b200he_batch *a, co
     }
     A.reduce_every = (u32)(run < 1 ? 1 : run > 0x7fffffff ? 0x7fffffff : run);
     constexpr int TI = 2, TJ = 2;
-    const u64 ti = (rows + TI - 1) / TI, tj = (cols + TJ - 1) / TJ, cblocks = (LN + 255) / 256;
+    const u64 ti = (rows + TI - 1) / TI, tj = (cols + TJ - 1) / TJ, cblocks = (LN + B200HE_MAC_THREADS - 1) / B200HE_MAC_THREADS;
     if (ti * tj * cblocks >= (u64(1) << 31)) return fail("matmul_accumulate: grid too large");
     A.tiles_j = (u32)tj;
     A.ntiles = (u32)(ti * tj);
-    LAUNCH(c, B200HE_KERN_TENSOR_MAC, (k_tensor_mac<TI, TJ>), (unsigned)(ti * tj * cblocks), 256, 0, c->T, A);
+    LAUNCH(c, B200HE_KERN_TENSOR_MAC, (k_tensor_mac<TI, TJ>), (unsigned)(ti * tj * cblocks), B200HE_MAC_THREADS, 0, c->T, A);
     LAUNCH_CHECK();
-    if (c->prof) {   // 4 wide multiply-accumulates per coefficient and term on the integer pipe; every operand read once, results written once
-        c->work_int[B200HE_KERN_TENSOR_MAC] += (double)rows * cols * inner * 4.0 * 0.5 * LN;
+    if (c->prof) {   // 4 multiply-accumulates per coefficient and term (0.5 butterfly-equivalents each) on the limb's pipe; every operand read once, results written once
+        for (int l = 0; l < a->L; l++) (c->mods[l].dp ? c->work_dp : c->work_int)[B200HE_KERN_TENSOR_MAC] += (double)rows * cols * inner * 4.0 * 0.5 * c->N;
         c->work_bytes[B200HE_KERN_TENSOR_MAC] += ((double)(rows + cols) * inner * 2.0 + (double)rows * cols * 3.0) * LN * 8;
     }
     return 0;

@@ -166,15 +166,97 @@ __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 x, u64 y)
 }
 // any 128-bit value -> canonical residue: (hi mod q) * (2^64 mod q) + (lo mod q)
 __device__ __forceinline__ u64 fold128(u64 lo, u64 hi, const Mod &m, u64 r64q) { return mad_mod(reduce64(hi, m), r64q, reduce64(lo, m), m); }
-template <int TI, int TJ> __global__ void __launch_bounds__(256) k_tensor_mac(Tables T, MacArgs A)
+// FP64-domain instance (moduli below 2^46, modarith.cuh): a residue splits exactly into two halves below 2^23 held in
+// doubles, a 46-bit product becomes four partial products below 2^46, and every accumulator is three doubles (weights
+// 1, 2^23, 2^46) fed by DFMA -- exact while the sums stay below 2^53, i.e. for runs of MAC_DP_RUN terms, after which each
+// double is reduced modulo q in place (x - rint(x/q) q, exact).  4 DFMA per product against ~5 IMAD.WIDE + carries.
+#define B200HE_MAC_DP_RUN 16   /* the middle accumulator of c1 gains 4 partial products < 2^46 per term: 16 * 2^48 + q < 2^53 */
+struct DpHalves { double lo, hi; };
+__device__ __forceinline__ DpHalves dp_split23(u64 x) { return DpHalves{ dp_from(x & 0x7fffffull), dp_from(x >> 23) }; }
+struct DpAcc {
+    double ll, mid, hh;
+    __device__ __forceinline__ void mac(const DpHalves &a, const DpHalves &b)
+    {
+        ll = __fma_rn(a.lo, b.lo, ll);
+        mid = __fma_rn(a.lo, b.hi, mid);
+        mid = __fma_rn(a.hi, b.lo, mid);
+        hh = __fma_rn(a.hi, b.hi, hh);
+    }
+    __device__ __forceinline__ void reduce(const Mod &m)
+    {
+        ll = dp_reduce(ll, m.dqinv, m.dnq);
+        mid = dp_reduce(mid, m.dqinv, m.dnq);
+        hh = dp_reduce(hh, m.dqinv, m.dnq);
+    }
+    // ll + 2^23 mid + 2^46 hh mod q, canonical
+    __device__ __forceinline__ u64 finish(const Mod &m)
+    {
+        reduce(m);
+        const double w = 8388608.0, wq = 8388608.0 * m.dqinv;   // 2^23 RN(1/q) = RN(2^23 / q) exactly
+        const double t = __dadd_rn(dp_mul(hh, w, wq, m.dnq), mid);
+        return dp_canon(__dadd_rn(dp_mul(t, w, wq, m.dnq), ll), m);
+    }
+};
+template <int TI, int TJ> __device__ __forceinline__ void tensor_mac_dp(const Tables &T, const MacArgs &A, const Mod &m, size_t ce, u32 i0, u32 j0)
 {
-    const size_t N = T.N, LN = (size_t)A.L * N;
-    const u32 tile = blockIdx.x % A.ntiles, cb = blockIdx.x / A.ntiles;
-    const size_t ce = (size_t)cb * blockDim.x + threadIdx.x;   // coefficient index within [L][N]
-    if (ce >= LN) return;
-    const Mod m = T.mods[ce / N];
+    const size_t LN = (size_t)A.L * T.N;
+    DpAcc acc[TI][TJ][3];
+#pragma unroll
+    for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+        for (int tj = 0; tj < TJ; tj++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[ti][tj][c] = DpAcc{ 0.0, 0.0, 0.0 };
+    size_t ia[TI], jb[TJ];
+#pragma unroll
+    for (int ti = 0; ti < TI; ti++) ia[ti] = (size_t)(i0 + ti < A.rows ? i0 + ti : A.rows - 1) * A.inner;
+#pragma unroll
+    for (int tj = 0; tj < TJ; tj++) jb[tj] = (size_t)(j0 + tj < A.cols ? j0 + tj : A.cols - 1) * A.inner;
+    u32 run = 0;
+    for (u32 k = 0; k < A.inner; k++) {
+        DpHalves a0[TI], a1[TI];
+#pragma unroll
+        for (int ti = 0; ti < TI; ti++) {
+            const u64 *pa = A.a + (ia[ti] + k) * A.a_stride + ce;
+            a0[ti] = dp_split23(ldg1(pa));
+            a1[ti] = dp_split23(ldg1(pa + LN));
+        }
+#pragma unroll
+        for (int tj = 0; tj < TJ; tj++) {
+            const u64 *pb = A.b + (jb[tj] + k) * A.b_stride + ce;
+            const DpHalves b0 = dp_split23(ldg1(pb)), b1 = dp_split23(ldg1(pb + LN));
+#pragma unroll
+            for (int ti = 0; ti < TI; ti++) {
+                acc[ti][tj][0].mac(a0[ti], b0);
+                acc[ti][tj][1].mac(a0[ti], b1);
+                acc[ti][tj][1].mac(a1[ti], b0);
+                acc[ti][tj][2].mac(a1[ti], b1);
+            }
+        }
+        if (++run == B200HE_MAC_DP_RUN && k + 1 < A.inner) {
+            run = 0;
+#pragma unroll
+            for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+                for (int tj = 0; tj < TJ; tj++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[ti][tj][c].reduce(m);
+        }
+    }
+#pragma unroll
+    for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+        for (int tj = 0; tj < TJ; tj++) {
+            if (i0 + ti >= A.rows || j0 + tj >= A.cols) continue;
+            u64 *o = A.out + ((size_t)(i0 + ti) * A.cols + (j0 + tj)) * A.out_stride + ce;
+#pragma unroll
+            for (int c = 0; c < 3; c++) o[(size_t)c * LN] = acc[ti][tj][c].finish(m);
+        }
+}
+template <int TI, int TJ> __device__ __forceinline__ void tensor_mac_int(const Tables &T, const MacArgs &A, const Mod &m, size_t ce, u32 i0, u32 j0)
+{
+    const size_t LN = (size_t)A.L * T.N;
     const u64 r64q = reduce64(m.nq, m);   // 2^64 mod q
-    const u32 i0 = (tile / A.tiles_j) * TI, j0 = (tile % A.tiles_j) * TJ;
     u64 lo[TI][TJ][3], hi[TI][TJ][3];
 #pragma unroll
     for (int ti = 0; ti < TI; ti++)
@@ -234,6 +316,20 @@ template <int TI, int TJ> __global__ void __launch_bounds__(256) k_tensor_mac(Ta
 #pragma unroll
             for (int c = 0; c < 3; c++) o[(size_t)c * LN] = fold128(lo[ti][tj][c], hi[ti][tj][c], m, r64q);
         }
+}
+// a block covers MAC_THREADS consecutive coefficients of one limb ([L][N], N a multiple of the block size): the modulus,
+// and with it the arithmetic domain, is uniform over the block
+#define B200HE_MAC_THREADS 128
+template <int TI, int TJ> __global__ void __launch_bounds__(B200HE_MAC_THREADS, 4) k_tensor_mac(Tables T, MacArgs A)
+{
+    const size_t N = T.N, LN = (size_t)A.L * N;
+    const u32 tile = blockIdx.x % A.ntiles, cb = blockIdx.x / A.ntiles;
+    const size_t ce = (size_t)cb * blockDim.x + threadIdx.x;   // coefficient index within [L][N]
+    if (ce >= LN) return;
+    const Mod m = T.mods[ce / N];
+    const u32 i0 = (tile / A.tiles_j) * TI, j0 = (tile % A.tiles_j) * TJ;
+    if (m.dp) tensor_mac_dp<TI, TJ>(T, A, m, ce, i0, j0);
+    else tensor_mac_int<TI, TJ>(T, A, m, ce, i0, j0);
 }
 
 // ------------------------------------------------------------------------------------ K8
