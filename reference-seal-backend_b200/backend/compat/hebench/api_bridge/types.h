@@ -15,7 +15,7 @@
 
 #define HEBENCH_MAX_OP_PARAMS 32
 #define HEBENCH_MAX_BUFFER_SIZE 256
-#define HEBENCH_MAX_CATEGORY_PARAMS 16
+#define HEBENCH_MAX_CATEGORY_PARAMS (HEBENCH_MAX_OP_PARAMS * 2)
 
 #define HEBENCH_ECODE_SUCCESS 0
 #define HEBENCH_ECODE_CRITICAL_ERROR 0x7fffffff
@@ -96,7 +96,7 @@ struct CategoryParams {
             uint64_t warmup_iterations_count;
         } latency;
         struct {
-            uint64_t data_count[HEBENCH_MAX_OP_PARAMS / 2];
+            uint64_t data_count[HEBENCH_MAX_OP_PARAMS];
         } offline;
     };
 };
@@ -111,6 +111,15 @@ struct BenchmarkDescriptor {
     Security security;
     int64_t other;
 };
+
+// The layout the plugin's descriptors are exchanged in.  These are the upstream sizes AS RECALLED (the upstream header
+// cannot be fetched offline): one 64-bit minimum test time, then a union of 2 * HEBENCH_MAX_OP_PARAMS reserved words.  A
+// build against the real api-bridge (CMakeLists.txt, -DAPI_BRIDGE_INSTALL_DIR) does not include this file at all; these
+// asserts make a silent drift of the restated structs impossible.
+static_assert(sizeof(_FlexibleData) == 24, "Handle / DataBuffer: pointer, size, tag");
+static_assert(sizeof(CategoryParams) == 8 + 8 * HEBENCH_MAX_CATEGORY_PARAMS, "CategoryParams: min_test_time_ms + reserved[]");
+static_assert(sizeof(WorkloadParam) == 8 + HEBENCH_MAX_BUFFER_SIZE + 8, "WorkloadParam: type (padded), name, value");
+static_assert(sizeof(BenchmarkDescriptor) == 16 + sizeof(CategoryParams) + 24, "BenchmarkDescriptor layout");
 
 }   // namespace APIBridge
 }   // namespace hebench

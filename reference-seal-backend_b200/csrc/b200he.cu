@@ -15,6 +15,8 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -127,6 +129,8 @@ struct b200he_ctx {
         unsigned char chunk[4] = { 0, 0, 0, 0 };    // source chunk (2^lognl coefficients) of every output chunk
     };
     std::map<u32, GalTab> galtab;
+    std::set<b200he_batch *> batches;   // live batches: orphaned (ctx = NULL, no storage) when the context goes first
+    std::mutex batches_mtx;
     uint64_t launches = 0;
     bool prof = false;
     std::vector<ProfRec> recs;
@@ -149,8 +153,14 @@ struct b200he_batch {
     uint64_t count = 0;
     int size = 0, L = 0, ntt = 0;
     double scale = 1.0;
-    size_t ct_words() const { return (size_t)size * L * ctx->N; }
+    u32 n_poly = 0;   // N of the owning context (kept so that the shape queries survive the context)
+    size_t ct_words() const { return (size_t)size * L * n_poly; }
 };
+// every entry that reaches a context THROUGH a batch goes through this: a batch that outlived its context is an error
+#define LIVE(b, what)                                                                              \
+    do {                                                                                           \
+        if (!(b)->ctx) return fail("%s: the batch's context has been destroyed", what);            \
+    } while (0)
 
 static inline void prof_pre(b200he_ctx *c, int cls)
 {
@@ -383,19 +393,27 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
     }
     c->c = logn - c->lognl;
     c->t = plain_modulus;
-    if (scheme == B200HE_BFV && init_behz(c, mv, pv)) { delete c; return -1; }
-    if (build_tables(c, mv, pv)) { delete c; return -1; }
-    if (scheme == B200HE_BFV && upload_behz(c)) { delete c; return -1; }
+    // every failure below releases what has been set up so far through b200he_ctx_destroy (tables, BEHZ constants, stream,
+    // pinned staging); the error text of the failing step is kept
+    auto bail = [&](int rc) {
+        const std::string keep = g_err;
+        b200he_ctx_destroy(c);
+        g_err = keep;
+        return rc ? rc : -1;
+    };
+    if (scheme == B200HE_BFV && init_behz(c, mv, pv)) return bail(-1);
+    if (build_tables(c, mv, pv)) return bail(-1);
+    if (scheme == B200HE_BFV && upload_behz(c)) return bail(-1);
 #ifndef B200HE_EMU
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("ctx_create: stream"); }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("ctx_create: stream"));
     c->own_stream = true;
 #endif
-    if (int rc = set_smem_attrs(c)) { delete c; return rc; }
+    if (int rc = set_smem_attrs(c)) return bail(rc);
     // pinned staging for load()/store() (page-locking 64 MB takes tens of milliseconds: not inside the first load)
-    if (stage_init(c, 0)) { delete c; return -1; }
+    if (stage_init(c, 0)) return bail(-1);
     // the tables were uploaded with synchronous copies from pageable memory (NULL stream): make sure they have landed
     // before the first kernel on the context's non-blocking stream can run
-    if (cudaDeviceSynchronize() != cudaSuccess) { delete c; return fail("ctx_create: device synchronisation failed"); }
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail("ctx_create: device synchronisation failed"));
     *out = c;
     return 0;
 }
@@ -404,7 +422,17 @@ extern "C" void b200he_ctx_destroy(b200he_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    {   // batches that outlive the context keep their handle but lose their storage: later calls on them fail cleanly
+        std::lock_guard<std::mutex> lock(c->batches_mtx);
+        for (b200he_batch *b : c->batches) {
+            b->ctx = nullptr;
+            b->d = nullptr;
+            b->cap_words = 0;
+            b->count = 0;
+        }
+        c->batches.clear();
+    }
     for (auto &r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (c->relin) cudaFree(c->relin);
     for (auto &kv : c->gal) cudaFree(kv.second);
@@ -550,17 +578,27 @@ extern "C" int b200he_batch_create(b200he_ctx *c, b200he_batch **out)
     if (!c || !out) return fail("batch_create: NULL argument");
     b200he_batch *b = new b200he_batch;
     b->ctx = c;
+    b->n_poly = c->N;
+    {
+        std::lock_guard<std::mutex> lock(c->batches_mtx);
+        c->batches.insert(b);
+    }
     *out = b;
     return 0;
 }
 extern "C" void b200he_batch_destroy(b200he_batch *b)
 {
     if (!b) return;
-    b->ctx->pool.put(b->d);
+    if (b200he_ctx *c = b->ctx) {   // (an orphaned batch owns nothing: its block went with the context's pool)
+        c->pool.put(b->d);
+        std::lock_guard<std::mutex> lock(c->batches_mtx);
+        c->batches.erase(b);
+    }
     delete b;
 }
 static int batch_shape(b200he_batch *b, uint64_t count, int size, int L, int ntt, double scale)
 {
+    LIVE(b, "batch");
     b200he_ctx *c = b->ctx;
     if (size < 1 || size > 3) return fail("batch: size %d out of range", size);
     const int Lmax = c->K > 1 ? (int)c->K - 1 : 1;
@@ -588,6 +626,7 @@ extern "C" int b200he_batch_resize(b200he_batch *b, uint64_t count, int size, in
 extern "C" int b200he_batch_upload(b200he_batch *b, uint64_t first, uint64_t n, const uint64_t *host)
 {
     if (!b || !host) return fail("batch_upload: NULL argument");
+    LIVE(b, "batch_upload");
     if (first + n > b->count) return fail("batch_upload: range [%llu,%llu) exceeds count %llu", (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)b->count);
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaMemcpyAsync(b->d + first * b->ct_words(), host, n * b->ct_words() * 8, cudaMemcpyHostToDevice, b->ctx->stream));
@@ -596,6 +635,7 @@ extern "C" int b200he_batch_upload(b200he_batch *b, uint64_t first, uint64_t n, 
 extern "C" int b200he_batch_download(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host)
 {
     if (!b || !host) return fail("batch_download: NULL argument");
+    LIVE(b, "batch_download");
     if (first + n > b->count) return fail("batch_download: range exceeds count");
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaMemcpyAsync(host, b->d + first * b->ct_words(), n * b->ct_words() * 8, cudaMemcpyDeviceToHost, b->ctx->stream));
@@ -606,6 +646,7 @@ extern "C" int b200he_batch_download(const b200he_batch *b, uint64_t first, uint
 extern "C" int b200he_batch_download_async(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *host)
 {
     if (!b || !host) return fail("batch_download_async: NULL argument");
+    LIVE(b, "batch_download_async");
     if (first + n > b->count) return fail("batch_download_async: range exceeds count");
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaMemcpyAsync(host, b->d + first * b->ct_words(), n * b->ct_words() * 8, cudaMemcpyDeviceToHost, b->ctx->stream));
@@ -649,6 +690,7 @@ template <class F> static void host_parallel(size_t n, F fn)
 extern "C" int b200he_batch_upload_scattered(b200he_batch *b, uint64_t first, uint64_t n, const uint64_t *const *host)
 {
     if (!b || (!host && n)) return fail("batch_upload_scattered: NULL argument");
+    LIVE(b, "batch_upload_scattered");
     if (first + n > b->count) return fail("batch_upload_scattered: range exceeds count");
     if (!n) return 0;
     for (uint64_t i = 0; i < n; i++)
@@ -672,6 +714,7 @@ extern "C" int b200he_batch_upload_scattered(b200he_batch *b, uint64_t first, ui
 extern "C" int b200he_batch_download_scattered(const b200he_batch *b, uint64_t first, uint64_t n, uint64_t *const *host)
 {
     if (!b || (!host && n)) return fail("batch_download_scattered: NULL argument");
+    LIVE(b, "batch_download_scattered");
     if (first + n > b->count) return fail("batch_download_scattered: range exceeds count");
     if (!n) return 0;
     for (uint64_t i = 0; i < n; i++)
@@ -705,6 +748,8 @@ extern "C" int b200he_batch_copy_from(b200he_batch *dst, const b200he_batch *src
 {
     if (!dst || !src) return fail("batch_copy_from: NULL argument");
     if (dst == src) return 0;
+    LIVE(dst, "batch_copy_from");
+    LIVE(src, "batch_copy_from");
     b200he_ctx *cd = dst->ctx, *cs = src->ctx;
     if (cd->N != cs->N || cd->K != cs->K || cd->scheme != cs->scheme) return fail("batch_copy_from: contexts differ in parameters");
     TRY(batch_shape(dst, src->count, src->size, src->L, src->ntt, src->scale));
@@ -744,7 +789,11 @@ struct OutBuf {
     b200he_batch *out;
     b200he_batch tmp;
     bool aliased;
-    OutBuf(b200he_batch *o, const b200he_batch *a, const b200he_batch *b = nullptr) : out(o), aliased(o == a || o == b) { tmp.ctx = o->ctx; }
+    OutBuf(b200he_batch *o, const b200he_batch *a, const b200he_batch *b = nullptr) : out(o), aliased(o == a || o == b)
+    {
+        tmp.ctx = o->ctx;   // (a scratch handle on the stack: not registered with the context, never outlives the call)
+        tmp.n_poly = o->n_poly;
+    }
     int shape(uint64_t count, int size, int L, int ntt, double scale)
     {
         return batch_shape(aliased ? &tmp : out, count, size, L, ntt, scale);
@@ -881,6 +930,7 @@ static int add_sub(b200he_ctx *c, const b200he_batch *a, const uint32_t *ai, con
     TRY(da.set(ai, n, a->count, what));
     TRY(db.set(bi, n, b->count, what));
     const int smin = a->size < b->size ? a->size : b->size, smax = a->size < b->size ? b->size : a->size;
+    if (sub && b->size > a->size) return fail("sub: size(b) > size(a) is not supported");   // before out is reshaped or anything is enqueued
     OutBuf ob(out, a, b);
     TRY(ob.shape(n, smax, a->L, a->ntt, a->scale));
     if (!n) { ob.commit(); return 0; }
@@ -896,7 +946,6 @@ static int add_sub(b200he_ctx *c, const b200he_batch *a, const uint32_t *ai, con
     if (c->prof) c->work_bytes[B200HE_KERN_ELEMENTWISE] += (double)n * smin * 3.0 * LN * 8;
     if (smax > smin) {   // the longer operand's extra polynomials pass through (negated for b in a - b)
         const b200he_batch *big = a->size > b->size ? a : b;
-        if (sub && big == b) return fail("sub: size(b) > size(a) is not supported");
         CopyArgs C{};
         C.src = big->d + smin * LN; C.dst = ob.ptr() + smin * LN; C.idx = (big == a) ? da.d : db.d;
         C.src_stride = big->ct_words(); C.dst_stride = smax * LN; C.polys = smax - smin; C.L_in = a->L; C.L_out = a->L; C.n = n;

@@ -126,7 +126,7 @@ class Batch:
 
     def __del__(self):
         try:
-            if self.h and self.ctx.h:
+            if self.h:   # safe after Context.close(): the library orphans the batches of a destroyed context
                 self.lib.b200he_batch_destroy(self.h)
         except Exception:
             pass

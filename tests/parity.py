@@ -125,6 +125,23 @@ def case_copy_between_contexts(env, n=3):
     other.close()
 
 
+def case_batch_outlives_context(env):
+    """a batch whose context was destroyed first: every call on it fails cleanly, destroying it is harmless"""
+    import pytest
+    other = hb.Context(env.scheme, env.N, env.moduli, env.orc.psi(), env.t, lib=env.ctx.lib)
+    x = env.rand_ct(2)
+    b = other.batch(x, size=2, L=env.Ltop)
+    other.close()
+    assert b.count == 0
+    for call in (lambda: other._ck(b.lib.b200he_batch_resize(b.h, 1, 2, env.Ltop, 1, 1.0)),
+                 lambda: other._ck(b.lib.b200he_batch_download(b.h, 0, 0, x.ctypes.data)),
+                 lambda: hb.Batch(env.ctx).copy_from(b),
+                 lambda: env.ctx.add(b, b)):
+        with pytest.raises(hb.B200HEError):
+            call()
+    del b   # b200he_batch_destroy on the orphan
+
+
 def case_extremes(env):
     """Worst-case magnitudes for the lazy-reduction schedules of both arithmetic domains (integer pipe, and the FP64
     domain of primes below 2^46): every residue q-1, every residue 0, alternating q-1 / 0 and q-1 / 1 patterns, with
@@ -396,6 +413,10 @@ def case_errors(env):
             env.ctx.add(x, y)        # different levels
     with pytest.raises(hb.B200HEError):
         env.ctx.add(x, x, ai=[3], bi=[0])   # index out of range
+    out = env.batch(env.rand_ct(1, L=L), L=L)
+    with pytest.raises(hb.B200HEError):
+        env.ctx.sub(x, x3, out=out)         # size(b) > size(a): rejected before `out` is touched
+    assert out.size == 2 and out.count == 1
     # the fused entry reports what the two calls would: last level, and size-2 input = plain rescale
     x1 = env.batch(env.rand_ct(1, size=3, L=1), size=3, L=1)
     with pytest.raises(hb.B200HEError):

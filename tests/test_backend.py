@@ -104,3 +104,24 @@ def test_baseline_config_shapes_on_gpu(built):
     for extra in runs:
         p = subprocess.run([HARNESS, "--backend_lib_path", PLUGIN] + extra, capture_output=True, text=True, timeout=1500)
         assert "[ Info    ] Failed: 0" in p.stdout and "Total: 1" in p.stdout, p.stdout[-3000:]
+
+
+def test_cmake_project_configures_offline_and_rejects_missing_seal(tmp_path):
+    """the CMake project with the reference's -D{SEAL,API_BRIDGE}_INSTALL_DIR options
+    (R/cmake/utils/import-library.cmake:54-66).  Offline it configures with the stand-ins; a SEAL prefix that holds no SEAL
+    is a hard error, as in the reference (the real-SEAL adapter hostfhe/seal_adapter.cpp cannot be compiled here)."""
+    import shutil
+    if not shutil.which("cmake"):
+        pytest.skip("cmake not installed")
+    src = os.path.join(ROOT, "reference-seal-backend_b200")
+    env = dict(os.environ, CXX="g++", CUDAHOSTCXX="g++")
+    p = subprocess.run(["cmake", "-S", src, "-B", str(tmp_path / "b"), "-G", "Ninja"], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "host crypto: hostfhe stand-in" in p.stdout and "api-bridge: backend/compat restatement" in p.stdout
+    q = subprocess.run(["cmake", "-S", src, "-B", str(tmp_path / "c"), "-G", "Ninja", "-DSEAL_INSTALL_DIR=" + str(tmp_path / "nowhere")],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert q.returncode != 0 and "FAILED TO FIND PRE-INSTALLED SEAL" in q.stderr
+    adapter = open(os.path.join(src, "hostfhe", "seal_adapter.cpp")).read()
+    hdr = open(os.path.join(src, "hostfhe", "hostfhe.h")).read()
+    for fn in re.findall(r"\b(hfhe_[a-z0-9_]+)\s*\(", hdr):   # the adapter implements the whole hostfhe.h interface
+        assert re.search(r'extern "C" [^;{]*\b' + fn + r"\s*\(", adapter), fn

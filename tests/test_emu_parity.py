@@ -50,6 +50,10 @@ def test_copy_between_contexts(ckks):
     parity.case_copy_between_contexts(ckks)
 
 
+def test_batch_outlives_context(ckks):
+    parity.case_batch_outlives_context(ckks)
+
+
 def test_matmul_accumulate(ckks):
     parity.case_matmul_accumulate(ckks)
 

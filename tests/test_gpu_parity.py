@@ -62,6 +62,10 @@ def test_copy_between_contexts(ckks):
     parity.case_copy_between_contexts(ckks)
 
 
+def test_batch_outlives_context(ckks):
+    parity.case_batch_outlives_context(ckks)
+
+
 def test_matmul_accumulate(ckks):
     parity.case_matmul_accumulate(ckks, rows=5, inner=9, cols=4)
     if ckks.Ltop > 2:
