@@ -306,6 +306,10 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-side group for the one wait that must not occupy the GPUs: while rank 0 drives the plugin over all the GPUs,
+        # the other ranks' processes must not keep an NCCL barrier kernel spinning on theirs (kernels of different
+        # processes time-slice a GPU: the plugin would get half of it)
+        cpu_group = dist.new_group(backend="gloo")
     ranks = Ranks(dist, device=torch.device("cuda", local))
 
     host = Host(CKKS, N_POLY, DEPTH, COEFF_BITS, COEFF_BITS, seed=SEED)
@@ -485,7 +489,8 @@ def run_b200(args):
     names = select_configs(args.configs, world)
     if rank != 0:
         if names:
-            ranks.barrier()   # rank 0 drives the plugin's own multi-GPU path over all the GPUs meanwhile
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)   # rank 0 drives the plugin's own multi-GPU path over all the GPUs meanwhile
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -552,7 +557,7 @@ def run_b200(args):
         block = run_plugin_configs(names, world, peak, bf_int_peak, bf_dp_peak, budget_s=args.configs_budget)
         line["configs" if world == 1 else "strong_scaling"] = block
         if dist is not None:
-            ranks.barrier()
+            dist.barrier(group=cpu_group)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

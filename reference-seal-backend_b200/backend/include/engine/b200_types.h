@@ -4,6 +4,9 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <new>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "b200he.h"
@@ -19,9 +22,17 @@ struct Plaintext {
     int L        = 0;      // RNS limbs (CKKS); 0 for BFV
     double scale = 1.0;
 };
+// allocator whose resize() leaves new words uninitialised: a result ciphertext is overwritten in full by store(), and
+// zero-filling gigabytes first costs as much as the copy itself
+template <class T> struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { typedef DefaultInitAllocator<U> other; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... Args> void construct(U *p, Args &&...args) { ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...); }
+};
 // host image of seal::Ciphertext: uint64[size][L][N]
 struct Ciphertext {
-    std::vector<std::uint64_t> data;
+    std::vector<std::uint64_t, DefaultInitAllocator<std::uint64_t>> data;
     int size     = 0;
     int L        = 0;
     bool ntt     = false;

@@ -669,12 +669,13 @@ static int stage_init(b200he_ctx *c, size_t ct_bytes)
     c->stage_bytes = want;
     return 0;
 }
-// run fn(i) for i in [0, n) on a few host threads (the copies are memory-bound: a handful of cores saturate DRAM)
+// run fn(i) for i in [0, n) on a few host threads (the copies are memory-bound -- and, into fresh pageable destinations,
+// page-fault-bound: up to 16 threads)
 template <class F> static void host_parallel(size_t n, F fn)
 {
     size_t T = std::thread::hardware_concurrency();
     if (const char *e = getenv("B200HE_HOST_THREADS")) T = (size_t)atoi(e);
-    if (T > 8) T = 8;
+    if (T > 16) T = 16;
     if (T > n) T = n;
     if (T <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);
