@@ -884,10 +884,10 @@ static int ntt_inv(b200he_ctx *c, const u64 *src, u64 *dst, size_t nlimbs, size_
     for (int l = 0; l < L; l++) n_dp += c->mods[mod_base + l].dp ? 1 : 0;
     const int kind = n_dp == 0 ? KIND_INT : n_dp == L ? KIND_DP : KIND_BOTH;
     PROF(c, B200HE_KERN_NTT_INV, launch_ntt_inv(geo(c), kind, c->T, src, dst, src_outer, dst_outer, L, mod_base, mode, F, nlimbs));
-    if (c->prof)   // fused relinearize+rescale last limb: two more operand tiles and two constant multiplies per coefficient
+    if (c->prof)   // fused relinearize+rescale last limb: one more operand tile and one constant multiply per coefficient
         for (int l = 0; l < L; l++)
-            work_add(c, B200HE_KERN_NTT_INV, mod_base + l, (double)nlimbs / L * (bfly_per_limb(c) + (F.add ? 2.0 * c->N : 0.0)),
-                     (double)nlimbs / L * (F.add ? 4.0 : 2.0) * c->N * 8);
+            work_add(c, B200HE_KERN_NTT_INV, mod_base + l, (double)nlimbs / L * (bfly_per_limb(c) + (F.sub ? 1.0 * c->N : 0.0)),
+                     (double)nlimbs / L * (F.sub ? 3.0 : 2.0) * c->N * 8);
     LAUNCH_CHECK();
     return 0;
 }
@@ -1177,6 +1177,11 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
         }
         A.key = key; A.acc = acc; A.rp = rp; A.L = L; A.K = (int)K; A.B = (int)nb;
         A.gal = gal ? gal->tab->d : nullptr;
+        if (rescale) {   // the last data limb leaves k_ks_inner as acc * s + c (the value the rescale's inverse transform rounds)
+            A.fuse_add = add0 + b0 * add_stride;
+            A.fuse_ct_stride = add_stride;
+            A.fuse_poly_stride = (size_t)(add1 - add0);
+        }
         // (the rounded special-prime limb comes out of k_ks_inner in coefficient form: rp)
         PROF(c, B200HE_KERN_KS_INNER, launch_ks_inner(geo(c), c->T, A, nb * (L + 1)));
         if (c->prof) {
@@ -1191,6 +1196,7 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
                 work_add(c, B200HE_KERN_KS_INNER, ki, nb * (ntts * bf + 2.0 * L * Nd), 2.0 * L * (c->mods[ki].dp ? 1.0 : 2.0) * Nd * 8);
             }
             work_add(c, B200HE_KERN_KS_INNER, 0, 0, nb * (2.0 * L + 2.0 * (L + 1)) * Nd * 8);
+            if (rescale) work_add(c, B200HE_KERN_KS_INNER, L - 1, nb * 2.0 * Nd, nb * 2.0 * Nd * 8);   // y = acc * s + c on the last data limb
         }
         if (cudaGetLastError() != cudaSuccess) { rc = fail("key_switch: k_ks_inner launch failed"); break; }
         ModDownArgs D{};
@@ -1205,12 +1211,11 @@ static int key_switch(b200he_ctx *c, int L, size_t B, const u64 *target, size_t 
             memcpy(D.gal_chunk, gal->tab->chunk, sizeof D.gal_chunk);
         }
         if (rescale) {
-            // last data limb: rp2 = iNTT(acc * s + addend) - u1 * s + q/2   (rounded last limb of the switched ciphertext)
+            // last data limb: rp2 = iNTT(acc * s + addend) - u1 * s + q/2   (rounded last limb of the switched ciphertext;
+            // acc * s + addend is what k_ks_inner left in the accumulator's limb L-1)
             u64 *rp2 = rp + nb * 2 * N;
             InvFuse F{};
-            F.add = add0 + b0 * add_stride + (size_t)(L - 1) * N;
-            F.add_ct_stride = add_stride; F.add_poly_stride = (size_t)(add1 - add0);
-            F.sub = rp; F.P = 2; F.x = (int)K - 1;
+            F.sub = rp; F.x = (int)K - 1;
             rc = ntt_inv(c, acc + (size_t)(L - 1) * N, rp2, nb * 2, (size_t)(L + 1) * N, N, 1, L - 1, INV_ADDHALF, &F);
             if (rc) break;
             D.rp2 = rp2; D.x2 = L - 1; D.nJ = L - 1; D.out_poly_stride = (size_t)(L - 1) * N;

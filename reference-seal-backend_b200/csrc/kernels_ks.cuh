@@ -28,6 +28,12 @@ struct KsInnerArgs {
     u64 *rp;               // [B][2][N]: rounded special-prime limb in coefficient form
     int L, K, B;           // B = ciphertexts in this launch
     const u32 *gal;        // Galois permutation of the NTT-form target, applied on load ([N], nullptr: none): see InvFuse::gal
+    // Fused relinearize + rescale: the accumulator limb of the LAST data modulus leaves this kernel as
+    //   y = acc * s + c        (s = q_sp^{-1} mod q_{L-1}, c = limb L-1 of the input ciphertext's component k, NTT form)
+    // -- the value whose inverse transform the rescale rounds -- so that the inverse transform that follows reads one
+    // tile instead of two and owns no pre-processing.  fuse_add + b * ct_stride + k * poly_stride + (L-1) N, or nullptr.
+    const u64 *fuse_add;
+    size_t fuse_ct_stride, fuse_poly_stride;
 };
 // lazy accumulator of the inner product (either domain) -> canonical residue
 __device__ __forceinline__ u64 acc_finish(u64 a, const Mod &m) { return m.dp ? dp_canon(as_d(a), m) : reduce_full(a, m); }
@@ -189,7 +195,24 @@ __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs
             x[reg + 1] = acc_finish(a.y, m);
         });
         contig_to_co(x, sm, tid);
-        for_pairs_co(tid, [&](int reg, int e) { st2(o + e, x[reg], x[reg + 1]); });
+        if (A.fuse_add && I == L - 1) {   // y = acc * s + c, canonical (CTA-uniform branch)
+            const u64 *cp = A.fuse_add + (size_t)b * A.fuse_ct_stride + (size_t)k * A.fuse_poly_stride + (size_t)I * N + off;
+            const ulonglong2 s = T.qinv[(size_t)(A.K - 1) * T.M + ki];
+            if constexpr (DP) {
+                const double sd = dp_from(s.x), sq = __dmul_rn(sd, m.dqinv);
+                for_pairs_co(tid, [&](int reg, int e) {
+                    const ulonglong2 cv = ldg2(cp + e);
+                    st2(o + e, dp_canon(__dadd_rn(dp_mul(dp_from(x[reg]), sd, sq, m.dnq), dp_from(cv.x)), m),
+                        dp_canon(__dadd_rn(dp_mul(dp_from(x[reg + 1]), sd, sq, m.dnq), dp_from(cv.y)), m));
+                });
+            } else {
+                for_pairs_co(tid, [&](int reg, int e) {
+                    const ulonglong2 cv = ldg2(cp + e);
+                    st2(o + e, add_mod(shoup(x[reg], s.x, s.y, m.q), cv.x, m.q), add_mod(shoup(x[reg + 1], s.x, s.y, m.q), cv.y, m.q));
+                });
+            }
+        } else
+            for_pairs_co(tid, [&](int reg, int e) { st2(o + e, x[reg], x[reg + 1]); });
         warp_sync();   // the slice is rewritten by the next component
     }
 }

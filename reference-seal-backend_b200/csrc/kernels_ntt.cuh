@@ -100,18 +100,15 @@ __device__ __forceinline__ u64 inv_finish(u64 v /* [0,2q) */, const Mod &m, int 
     if (mode == INV_ADDHALF) v = csub(v + (m.q >> 1), m.q);
     return v;
 }
-// Optional fusion around the inverse transform of limb w = (b, p) (b = w / P, p = w % P), used by the fused
-// relinearize + rescale for the last data limb j:
-//   input   y = src * s + add[b][p]          (s = q_x^{-1} mod q_j: the key-switch accumulator scaled and added to the
-//                                             input ciphertext, still in NTT form)
-//   output  iNTT(y) - ((sub[w] mod q_j) + fix) * s   (the mod-down correction applied in coefficient form: the
-//                                             transform is linear, so NTT(u) never has to be computed for this limb)
-// followed by the usual finish (INV_ADDHALF: + q_j / 2, the rounding of the rescale that follows).
+// Optional fusion around the inverse transform of limb w, used by the fused relinearize + rescale for the last data
+// limb j.  The input is y = acc * s + c (NTT form; k_ks_inner writes it, KsInnerArgs::fuse_add); this
+// kernel computes
+//   iNTT(y) - ((sub[w] mod q_j) + fix) * s      s = q_x^{-1} mod q_j, fix = q_j - (q_x / 2 mod q_j)
+// -- the mod-down correction applied in coefficient form: the transform is linear, so NTT(u) never has to be computed
+// for this limb -- followed by the usual finish (INV_ADDHALF: + q_j / 2, the rounding of the rescale that follows).
 struct InvFuse {
-    const u64 *add;        // nullptr: plain transform
-    size_t add_ct_stride, add_poly_stride;
-    const u64 *sub;        // [nlimbs][N] coefficient form (the rounded special-prime limb)
-    int P, x;              // polys per ciphertext; x = modulus id of the prime dropped by the key switch
+    const u64 *sub;        // [nlimbs][N] coefficient form (the rounded special-prime limb); nullptr: plain transform
+    int x;                 // modulus id of the prime dropped by the key switch
     // Galois automorphism applied on load (plain transform only): dst = iNTT(g(src)), g(src)[i] = src[gal[i]] -- the
     // target of a rotation's key switch enters the key switch without a permutation pass
     const u32 *gal;        // [N] or nullptr
@@ -132,6 +129,10 @@ template <int KIND> __device__ __forceinline__ Mod load_mod(const Tables &T, int
     if (KIND == KIND_DP) m.dp = 1;
     return m;
 }
+// (Measured on the B200 and dropped, C2 step, both k_ntt_inv launches together 0.358 ms with the plain loads below:
+//  the epilogue operand staged by a TMA bulk copy issued before the transform, as in k_moddown: 0.372 ms; a persistent
+//  variant with both input tiles of the next limb prefetched by TMA: 0.371 ms.  The warps of this kernel already overlap
+//  one another's load and compute phases; the extra CTA-wide synchronisation costs more than the hidden latency.)
 template <int LOGN, int C, int KIND>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, const u64 *__restrict__ src, u64 *__restrict__ dst,
                                                                    size_t src_outer, size_t dst_outer, int L, int mod_base, int mode, InvFuse F)
@@ -151,19 +152,17 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     ulonglong2 fs = make_ulonglong2(0, 0);
     u64 ffix = 0;
     if constexpr (C == 0 && KIND != KIND_INT) {
-        if (F.add && m.dp) {
-            // FP64-domain modulus: the fused pre- and post-processing (see InvFuse) stay in the domain -- scaling of the
-            // accumulator, the split lift of the rounded special-prime limb, its scaling and the subtraction -- and
-            // the result leaves it once, in the final store
+        if (F.sub && m.dp) {
+            // FP64-domain modulus: the fused post-processing (see InvFuse) stays in the domain -- the split lift of the
+            // rounded special-prime limb, its scaling and the subtraction -- and the result leaves it once, in the final store
             constexpr int NPL = Sched<LOGN>::NP - 1;
             const double nq = m.dnq, sd = dp_from(T.qinv[(size_t)F.x * T.M + mid].x), sq = __dmul_rn(sd, m.dqinv);
             const double fixd = dp_from(m.q - T.halfmod[(size_t)F.x * T.M + mid]), wq30 = 1073741824.0 * m.dqinv;
             const double half = mode == INV_ADDHALF ? dp_from(m.q >> 1) : 0.0;
-            const u64 *ad = F.add + (size_t)(w / F.P) * F.add_ct_stride + (size_t)(w % F.P) * F.add_poly_stride;
             for_pairs_co(tid, [&](int reg, int e) {
-                const ulonglong2 v = ldg2(in + e), a = ldg2(ad + e);
-                x[reg] = as_u(__dadd_rn(dp_mul(dp_from(v.x), sd, sq, nq), dp_from(a.x)));
-                x[reg + 1] = as_u(__dadd_rn(dp_mul(dp_from(v.y), sd, sq, nq), dp_from(a.y)));
+                const ulonglong2 v = ldg2(in + e);
+                x[reg] = as_u(dp_from(v.x));
+                x[reg + 1] = as_u(dp_from(v.y));
             });
             co_to_contig(x, sm, tid);
             ntt_inv_regs_split<LOGN, true, false, NPL, true, true>(x, sm, itw, m, tid, 0, 0, tl);
@@ -178,16 +177,11 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
             return;
         }
     }
-    if (F.add) {
+    if (F.sub) {
         fs = T.qinv[(size_t)F.x * T.M + mid];
         ffix = m.q - T.halfmod[(size_t)F.x * T.M + mid];
-        const u64 *ad = F.add + (size_t)(w / F.P) * F.add_ct_stride + (size_t)(w % F.P) * F.add_poly_stride + (size_t)r * NL;
-        for_pairs_co(tid, [&](int reg, int e) {
-            const ulonglong2 v = ldg2(in + e), a = ldg2(ad + e);
-            x[reg] = add_mod(shoup(v.x, fs.x, fs.y, m.q), a.x, m.q);
-            x[reg + 1] = add_mod(shoup(v.y, fs.x, fs.y, m.q), a.y, m.q);
-        });
-    } else if (F.gal) {
+    }
+    if (F.gal) {
         gather_pairs_co(x, in - (size_t)r * NL, F.gal + (size_t)r * NL, tid);
     } else {
         for_pairs_co(tid, [&](int reg, int e) {
@@ -206,7 +200,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
         cross_inv<LOGN>(x, sm, c, r, tid, itw, m);
     }
     // x: finished values in [0, 2q), pass-0 layout of chunk r
-    if (F.add) {
+    if (F.sub) {
         const u64 *sb = F.sub + (size_t)w * T.N + (size_t)r * NL;
         for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
             const ulonglong2 u = ldg2(sb + e);
@@ -217,4 +211,5 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_inv(Tables T, con
     }
     for_pairs_strided<LOGN>(tid, [&](int reg, int e) { st2(out + e, inv_finish(x[reg], m, mode), inv_finish(x[reg + 1], m, mode)); });
 }
+
 }   // namespace b200he

@@ -20,14 +20,14 @@ void launch_ntt_inv(const Geo &g, int kind, const Tables &T, const u64 *src, u64
 {
     const unsigned grid = (unsigned)(nlimbs << g.c);
     if (kind == KIND_INT) {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ntt_inv<LG, CC, KIND_INT>), grid, NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, src, dst,
-                                                 src_outer, dst_outer, L, mod_base, mode, F));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ntt_inv<LG, CC, KIND_INT>), grid, NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c,
+                                                 T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
     } else if (kind == KIND_DP) {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ntt_inv<LG, CC, KIND_DP>), grid, NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, src, dst,
-                                                 src_outer, dst_outer, L, mod_base, mode, F));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ntt_inv<LG, CC, KIND_DP>), grid, NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c,
+                                                 T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
     } else {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ntt_inv<LG, CC, KIND_BOTH>), grid, NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, src, dst,
-                                                 src_outer, dst_outer, L, mod_base, mode, F));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ntt_inv<LG, CC, KIND_BOTH>), grid, NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c,
+                                                 T, src, dst, src_outer, dst_outer, L, mod_base, mode, F));
     }
 }
 
