@@ -189,8 +189,12 @@ template <int LOGN> __device__ __forceinline__ void cross_collect(u64 (&x)[16], 
 // First c Cooley-Tukey stages across the chunks of a cluster.  In: x = pass-0 layout of chunk r, values < 2q.
 // Out: the same registers after global stages 0..c-1, values < (2 + 2c) q.  Twiddles: stage 0 tw[1]; stage 1 tw[2]
 // (chunks 0,1) and tw[3] (chunks 2,3).
-template <int LOGN>
-__device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, int tid, const ulonglong2 *__restrict__ tw, const Mod &m)
+// `hook` runs right before the second cluster barrier: the place from which a caller starts loads it needs after the cross
+// stages (k_ks_inner: the twiddles of the first local pass), so that they are not live across the radix-4 butterflies and
+// their latency hides behind the barrier.
+template <int LOGN, class Hook = NoHook>
+__device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, int tid, const ulonglong2 *__restrict__ tw, const Mod &m,
+                                          Hook &&hook = Hook())
 {
     const int own = 16 >> c;
     cross_publish<LOGN>(x, sm, c, r, tid);
@@ -244,6 +248,7 @@ __device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, i
             }
         });
     }
+    hook();
     cluster_sync();
     cross_collect<LOGN>(x, sm, c, r, tid);
 }
@@ -334,9 +339,9 @@ __device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, i
 // input transform, and run the c cross-chunk stages.  pre.pair() must return values < 2q; the result is < (2 + 2c) q
 // (Mod::dp moduli: converted to the FP64 domain right after the load).
 // REUSE: the CTA has used the transform buffer before (see ntt_fwd_regs_split).
-template <int LOGN, bool REUSE = false, class Pre>
+template <int LOGN, bool REUSE = false, class Pre, class Hook = NoHook>
 __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restrict__ src, int c, int r, int tid,
-                                               const ulonglong2 *__restrict__ tw, const Mod &m, Pre pre, u64 *sm)
+                                               const ulonglong2 *__restrict__ tw, const Mod &m, Pre pre, u64 *sm, Hook &&hook = Hook())
 {
     constexpr int NL = 1 << LOGN;
     const size_t off = (size_t)r * NL;
@@ -350,7 +355,7 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
     }
     if (c > 0) {
         if (REUSE) __syncthreads();
-        cross_fwd<LOGN>(x, sm, c, r, tid, tw, m);
+        cross_fwd<LOGN>(x, sm, c, r, tid, tw, m, hook);
     }
 }
 

@@ -89,19 +89,24 @@ __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs
             if (m.dp) to_dp_all(x);
         } else {
             const u64 *tp = A.tcoef + (size_t)b * A.tcoef_stride + (size_t)J * N;
+            // twiddles of the first local pass: next to the data loads for unsplit limbs; for clusters from inside the cross
+            // stages (before their second barrier), so that 28 registers are not live across the radix-2/4 butterflies
             TwRegs<LOGN, 0> t0;
-            load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
+            auto load_t0 = [&]() { load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r); };
+            if constexpr (C == 0) load_t0();
+            auto split = [&](auto pre) {
+                if constexpr (C == 0) load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, pre, sm);
+                else load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, pre, sm, load_t0);
+            };
             if constexpr (DP) {   // FP64 domain: digits of moduli up to 48 bits are lazy values as they are (2^48 + 14 q < 2^50)
-                if (T.mods[J].bits > 48)
-                    load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreLiftDp{ 1073741824.0 * m.dqinv, m.dnq }, sm);
-                else
-                    load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
+                if (T.mods[J].bits > 48) split(PreLiftDp{ 1073741824.0 * m.dqinv, m.dnq });
+                else split(PreNone());
             } else if (lift_wide(T.mods[J].q, m.q))
-                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce<true>{ m.q, m.r64 }, sm);
+                split(PreReduce<true>{ m.q, m.r64 });
             else if (T.mods[J].q > m.q)
-                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreReduce<false>{ m.q, m.r64 }, sm);
+                split(PreReduce<false>{ m.q, m.r64 });
             else
-                load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, PreNone(), sm);
+                split(PreNone());
             ntt_fwd_regs_split<LOGN, true>(x, sm, tw, m, tid, c, r, t0, prefetch_key0);
         }
         // x: the digit in NTT form, lazy (any 64-bit value congruent to it, or an FP64-domain value of magnitude < 14 q)

@@ -80,8 +80,15 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
     const u64 fix = m.q - T.halfmod[(size_t)A.x * T.M + j];
     const ulonglong2 qi = T.qinv[(size_t)A.x * T.M + j];
     u64 x[16];
+    // twiddles of the first local pass: next to the data loads for unsplit limbs; for clusters from inside the cross stages
+    // (before their second barrier), so that they are not live across the radix-2/4 butterflies (as in k_ks_inner)
     TwRegs<LOGN, 0> t0;
-    load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
+    auto load_t0 = [&]() { load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r); };
+    if constexpr (C == 0) load_t0();
+    auto split = [&](const u64 *src, auto pre) {
+        if constexpr (C == 0) load_fwd_split<LOGN>(x, src, c, r, tid, tw, m, pre, sm);
+        else load_fwd_split<LOGN>(x, src, c, r, tid, tw, m, pre, sm, load_t0);
+    };
     const u64 *bp = A.base + (size_t)b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + off;
     const u64 *ap = A.addend[p] ? A.addend[p] + (size_t)b * A.add_ct_stride + (size_t)j * N + off : nullptr;
     u64 *op = A.out + (size_t)b * A.out_ct_stride + (size_t)p * A.out_poly_stride + (size_t)j * N + off;
@@ -115,9 +122,9 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
             const double fix2 = dp_from(m.q - T.halfmod[(size_t)A.x2 * T.M + j]);
             const u64 *rp2 = A.rp2 + ((size_t)b * A.P + p) * N;
             if (w1 && T.mods[A.x2].bits <= 48)   // the usual case: special prime wide, last data prime narrow
-                load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreTwoDp<true, false>{ wq30, nq, dp_from(fix), fix2, sd, sq, rd, rq, rp2 }, sm);
+                split(rp, PreTwoDp<true, false>{ wq30, nq, dp_from(fix), fix2, sd, sq, rd, rq, rp2 });
             else
-                load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreTwoDp<true, true>{ wq30, nq, dp_from(fix), fix2, sd, sq, rd, rq, rp2 }, sm);
+                split(rp, PreTwoDp<true, true>{ wq30, nq, dp_from(fix), fix2, sd, sq, rd, rq, rp2 });
             ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
             contig_to_co(x, sm, tid);   // FP64-domain values, |x| < 14 q
             tma_bar_wait(bar, 0);
@@ -129,8 +136,8 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
             });
             return;
         }
-        if (w1) load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreReduceFixDp<true>{ wq30, nq, dp_from(fix) }, sm);
-        else load_fwd_split<LOGN>(x, rp, c, r, tid, tw, m, PreReduceFixDp<false>{ wq30, nq, dp_from(fix) }, sm);
+        if (w1) split(rp, PreReduceFixDp<true>{ wq30, nq, dp_from(fix) });
+        else split(rp, PreReduceFixDp<false>{ wq30, nq, dp_from(fix) });
         ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
         contig_to_co(x, sm, tid);
         tma_bar_wait(bar, 0);
@@ -155,11 +162,9 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
         const ulonglong2 ri = T.qinv[(size_t)A.x2 * T.M + j];
         const u64 fix2 = m.q - T.halfmod[(size_t)A.x2 * T.M + j];
         if (lift_wide(T.mods[A.x].q, m.q) || lift_wide(T.mods[A.x2].q, m.q))
-            load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
-                                 PreTwo<true>{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
+            split(A.rp + ((size_t)b * A.P + p) * N, PreTwo<true>{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N });
         else
-            load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m,
-                                 PreTwo<false>{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N }, sm);
+            split(A.rp + ((size_t)b * A.P + p) * N, PreTwo<false>{ m.q, m.r64, fix, fix2, qi, ri, A.rp2 + ((size_t)b * A.P + p) * N });
         ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
         canon_all(x, m);
         contig_to_co(x, sm, tid);
@@ -173,9 +178,9 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
         return;
     }
     if (lift_wide(T.mods[A.x].q, m.q))
-        load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix<true>{ m.q, m.r64, fix }, sm);
+        split(A.rp + ((size_t)b * A.P + p) * N, PreReduceFix<true>{ m.q, m.r64, fix });
     else
-        load_fwd_split<LOGN>(x, A.rp + ((size_t)b * A.P + p) * N, c, r, tid, tw, m, PreReduceFix<false>{ m.q, m.r64, fix }, sm);
+        split(A.rp + ((size_t)b * A.P + p) * N, PreReduceFix<false>{ m.q, m.r64, fix });
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     canon_all(x, m);
     contig_to_co(x, sm, tid);
