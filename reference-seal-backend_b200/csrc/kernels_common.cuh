@@ -166,6 +166,15 @@ __device__ __forceinline__ void cluster_sync() { cooperative_groups::this_cluste
 __device__ __forceinline__ u64 *cluster_peer(u64 *sm, int rank) { return cooperative_groups::this_cluster().map_shared_rank(sm, (unsigned)rank); }
 #endif
 
+// 4-way select / scatter by the (CTA-uniform) chunk rank, with constant register indices on every path
+__device__ __forceinline__ u64 sel4(int r, u64 a, u64 b, u64 c, u64 d) { return r == 0 ? a : r == 1 ? b : r == 2 ? c : d; }
+__device__ __forceinline__ void put4(int r, u64 v0, u64 v1, u64 v2, u64 v3, u64 &a, u64 &b, u64 &c, u64 &d)
+{
+    if (r == 0) a = v0;
+    else if (r == 1) b = v1;
+    else if (r == 2) c = v2;
+    else d = v3;
+}
 // publish the register pairs owned by other CTAs / fetch them back after the owners have pushed the results
 template <int LOGN> __device__ __forceinline__ void cross_publish(const u64 (&x)[16], u64 *sm, int c, int r, int tid)
 {
@@ -225,16 +234,30 @@ __device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, i
         u64 *peer[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) peer[q] = cluster_peer(sm, q);
+        // CTA r owns register pairs (4r, 4r+1) and (4r+2, 4r+3) = rows 2r and 2r+1 of the pass-0 layout.  All six peer
+        // values are requested before the first is used (one DSMEM latency, not two), the own operands are selected from
+        // the four candidate register groups so that no register index depends on r.
+        typedef Pass<LOGN, 0> G0;
         const ulonglong2 w1 = ld_tw(tw + 1), w2 = ld_tw(tw + 2), w3 = ld_tw(tw + 3);
-        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            if (reg / own != r) return;
-            ulonglong2 v[4];
+        int es[2];
+        ulonglong2 pv[2][4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = (q == r) ? make_ulonglong2(x[reg], x[reg + 1]) : ld2(peer[q] + swz(e));
+        for (int i = 0; i < 2; i++) {
+            es[i] = swz(G0::elem(tid, 2 * r + i, 0));
+            const ulonglong2 own2 = make_ulonglong2(sel4(r, x[2 * i], x[4 + 2 * i], x[8 + 2 * i], x[12 + 2 * i]),
+                                                    sel4(r, x[2 * i + 1], x[5 + 2 * i], x[9 + 2 * i], x[13 + 2 * i]));
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (q == r) pv[i][q] = own2;
+                else pv[i][q] = ld2(peer[q] + es[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
             u64 o[4][2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                u64 a0 = h ? v[0].y : v[0].x, a1 = h ? v[1].y : v[1].x, a2 = h ? v[2].y : v[2].x, a3 = h ? v[3].y : v[3].x;
+                u64 a0 = h ? pv[i][0].y : pv[i][0].x, a1 = h ? pv[i][1].y : pv[i][1].x, a2 = h ? pv[i][2].y : pv[i][2].x, a3 = h ? pv[i][3].y : pv[i][3].x;
                 ct_lazy(a0, a2, w1, m);
                 ct_lazy(a1, a3, w1, m);
                 ct_lazy(a0, a1, w2, m);
@@ -242,11 +265,11 @@ __device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, i
                 o[0][h] = a0; o[1][h] = a1; o[2][h] = a2; o[3][h] = a3;
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (q == r) { x[reg] = o[q][0]; x[reg + 1] = o[q][1]; }
-                else st2(peer[q] + swz(e), o[q][0], o[q][1]);
-            }
-        });
+            for (int q = 0; q < 4; q++)
+                if (q != r) st2(peer[q] + es[i], o[q][0], o[q][1]);
+            put4(r, o[0][0], o[1][0], o[2][0], o[3][0], x[2 * i], x[4 + 2 * i], x[8 + 2 * i], x[12 + 2 * i]);
+            put4(r, o[0][1], o[1][1], o[2][1], o[3][1], x[2 * i + 1], x[5 + 2 * i], x[9 + 2 * i], x[13 + 2 * i]);
+        }
     }
     hook();
     cluster_sync();
@@ -309,27 +332,39 @@ __device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, i
         u64 *peer[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) peer[q] = cluster_peer(sm, q);
+        // (same structure as cross_fwd: all six peer values requested first, own operands selected by r)
+        typedef Pass<LOGN, 0> G0;
         const ulonglong2 w2 = ld_tw(itw + 2), w3 = ld_tw(itw + 3);
-        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
-            if (reg / own != r) return;
-            ulonglong2 v[4];
+        int es[2];
+        ulonglong2 pv[2][4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = (q == r) ? make_ulonglong2(x[reg], x[reg + 1]) : ld2(peer[q] + swz(e));
+        for (int i = 0; i < 2; i++) {
+            es[i] = swz(G0::elem(tid, 2 * r + i, 0));
+            const ulonglong2 own2 = make_ulonglong2(sel4(r, x[2 * i], x[4 + 2 * i], x[8 + 2 * i], x[12 + 2 * i]),
+                                                    sel4(r, x[2 * i + 1], x[5 + 2 * i], x[9 + 2 * i], x[13 + 2 * i]));
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (q == r) pv[i][q] = own2;
+                else pv[i][q] = ld2(peer[q] + es[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
             u64 o[4][2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                u64 a0 = h ? v[0].y : v[0].x, a1 = h ? v[1].y : v[1].x, a2 = h ? v[2].y : v[2].x, a3 = h ? v[3].y : v[3].x;
+                u64 a0 = h ? pv[i][0].y : pv[i][0].x, a1 = h ? pv[i][1].y : pv[i][1].x, a2 = h ? pv[i][2].y : pv[i][2].x, a3 = h ? pv[i][3].y : pv[i][3].x;
                 gs_cross(a0, a1, w2, m);
                 gs_cross(a2, a3, w3, m);
                 inv_last(a0, a2, wn, m, o[0][h], o[2][h]);
                 inv_last(a1, a3, wn, m, o[1][h], o[3][h]);
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (q == r) { x[reg] = o[q][0]; x[reg + 1] = o[q][1]; }
-                else st2(peer[q] + swz(e), o[q][0], o[q][1]);
-            }
-        });
+            for (int q = 0; q < 4; q++)
+                if (q != r) st2(peer[q] + es[i], o[q][0], o[q][1]);
+            put4(r, o[0][0], o[1][0], o[2][0], o[3][0], x[2 * i], x[4 + 2 * i], x[8 + 2 * i], x[12 + 2 * i]);
+            put4(r, o[0][1], o[1][1], o[2][1], o[3][1], x[2 * i + 1], x[5 + 2 * i], x[9 + 2 * i], x[13 + 2 * i]);
+        }
     }
     cluster_sync();
     cross_collect<LOGN>(x, sm, c, r, tid);
