@@ -208,29 +208,7 @@ __device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, i
     const int own = 16 >> c;
     cross_publish<LOGN>(x, sm, c, r, tid);
     cluster_sync();
-    if (c == 1) {
-        // CTA r owns register pairs [4r, 4r + 4): pair i of those sits at offset base + (4r + i) G.  All four peer
-        // values are requested before the first is used (DSMEM latency paid once); the own operands are selected
-        // from the two candidate register groups so that no register index depends on r.
-        typedef Pass<LOGN, 0> G0;
-        // (limbs are split only into chunks of 8192 coefficients -- KERNEL_DISPATCH -- whose first pass holds 8 rows x 2 columns)
-        u64 *peer = cluster_peer(sm, r ^ 1);
-        const ulonglong2 w = ld_tw(tw + 1);
-        ulonglong2 pv[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) pv[i] = ld2(peer + swz(G0::elem(tid, 4 * r + i, 0)));
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const u64 o0 = r ? x[8 + 2 * i] : x[2 * i], o1 = r ? x[9 + 2 * i] : x[2 * i + 1];
-            u64 a0 = r ? pv[i].x : o0, a1 = r ? pv[i].y : o1;   // chunk 0
-            u64 b0 = r ? o0 : pv[i].x, b1 = r ? o1 : pv[i].y;   // chunk 1
-            ct_lazy(a0, b0, w, m);
-            ct_lazy(a1, b1, w, m);
-            st2(peer + swz(G0::elem(tid, 4 * r + i, 0)), r ? a0 : b0, r ? a1 : b1);
-            if (r) { x[8 + 2 * i] = b0; x[9 + 2 * i] = b1; }
-            else { x[2 * i] = a0; x[2 * i + 1] = a1; }
-        }
-    } else {
+    {   // c == 2 (clusters of two never come here: load_fwd_split computes their single cross stage from global memory)
         u64 *peer[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) peer[q] = cluster_peer(sm, q);
@@ -387,6 +365,31 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
     });
     if constexpr (!Pre::gives_dp) {
         if (m.dp) to_dp_all(x);
+    }
+    if (c == 1) {
+        // Clusters of two, forward direction: the one cross-chunk stage pairs offset e of chunk 0 with offset e of chunk 1,
+        // and both come straight from global memory.  Each CTA therefore loads the sibling chunk as well (served from L2:
+        // the sibling reads the same lines at the same time) and computes the stage for its own half -- one duplicated
+        // multiply per coefficient (half a stage of fourteen) against two cluster barriers and a DSMEM round trip.
+        // Measured on the B200 (C3 / C4 Val through the plugin): k_ks_inner -4 % / -10 %, k_moddown -8 % / -9 %.  (For
+        // clusters of four the same trade costs three multiplies per coefficient instead of one and four times the loads:
+        // they keep the DSMEM exchange of cross_fwd.)
+        const size_t offp = (size_t)(r ^ 1) * NL;
+        const ulonglong2 w = ld_tw(tw + 1);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            ulonglong2 p = pre.pair(ldg2(src + offp + e), offp + e);
+            if constexpr (!Pre::gives_dp) {
+                if (m.dp) { p.x = as_u(dp_from(p.x)); p.y = as_u(dp_from(p.y)); }
+            }
+            u64 a0 = r ? p.x : x[reg], a1 = r ? p.y : x[reg + 1];   // chunk 0
+            u64 b0 = r ? x[reg] : p.x, b1 = r ? x[reg + 1] : p.y;   // chunk 1
+            ct_lazy(a0, b0, w, m);
+            ct_lazy(a1, b1, w, m);
+            x[reg] = r ? b0 : a0;
+            x[reg + 1] = r ? b1 : a1;
+        });
+        hook();
+        return;
     }
     if (c > 0) {
         if (REUSE) __syncthreads();

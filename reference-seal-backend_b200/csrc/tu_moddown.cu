@@ -7,12 +7,15 @@ namespace b200he {
 void launch_moddown_kind(const Geo &g, int kind, const Tables &T, const ModDownArgs &D, size_t units)
 {
     const unsigned grid = (unsigned)(units << g.c);
+    // clusters of two exchange nothing in the forward direction (load_fwd_split computes their cross stage from global
+    // memory): the two CTAs of a limb are launched as ordinary CTAs, free to land on any SM
+    const unsigned cl = g.c == 1 ? 1u : 1u << g.c;
     if (kind == KIND_INT) {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, 1u << g.c, T, D));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, cl, T, D));
     } else if (kind == KIND_DP) {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_dp<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, 1u << g.c, T, D));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_dp<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, cl, T, D));
     } else {
-        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_mix<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, 1u << g.c, T, D));
+        KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown_mix<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, cl, T, D));
     }
 }
 

@@ -7,7 +7,7 @@ root=$(cd "$here/../.." && pwd)
 csrc="$root/reference-seal-backend_b200/csrc"
 obj="$here/obj"
 mkdir -p "$obj"
-FLAGS="-O2 -pthread -ffp-contract=off -std=c++17 -fPIC -DB200HE_EMU -I$root/tests -I$csrc -Wno-unknown-pragmas"
+FLAGS="$EMU_EXTRA -O2 -pthread -ffp-contract=off -std=c++17 -fPIC -DB200HE_EMU -I$root/tests -I$csrc -Wno-unknown-pragmas"
 pids=""
 for u in b200he tu_ntt tu_ks tu_moddown; do
     g++ $FLAGS -x c++ -c -o "$obj/$u.o" "$csrc/$u.cu" &
