@@ -62,7 +62,9 @@ public:
     DeviceBatchPtr upload(int g, const Ciphertext &src) const;
     DeviceBatchPtr uploadPlain(int g, const std::vector<Plaintext> &src) const;
     // D2H (blocks until the batch's stream has produced the data)
-    std::vector<Ciphertext> download(const DeviceBatch &b) const;
+    std::vector<Ciphertext> download(const DeviceBatch &b, std::shared_ptr<HostSlab> slab = nullptr) const;
+    // called by operate() once a result's kernels are enqueued and before it waits for them: host memory for store()
+    void prepareStore(ShardedCiphertexts &res) const;
     void syncAll() const;
     // split [0, n) into gpuCount() contiguous blocks
     std::vector<std::uint64_t> partition(std::uint64_t n) const;

@@ -247,6 +247,7 @@ Handle MatMultBenchmarkT<CKKS>::operate(Handle h_remote_packed, const ParameterI
     const LoadedMats &in = this->getEngine().template retrieveFromHandle<LoadedMats>(h_remote_packed);
     m_p_ctx_wrapper->beginOperate();
     ShardedCiphertexts out = m_algo == MatMultAlgo::Val ? operateVal(in) : m_algo == MatMultAlgo::Row ? operateRow(in) : operateCipherBatchAxis(in);
+    m_p_ctx_wrapper->prepareStore(out);
     m_p_ctx_wrapper->endOperate(1);
     return this->getEngine().template createHandle<ShardedCiphertexts>(sizeof(ShardedCiphertexts), ResultCipherTag, std::move(out));
 }

@@ -269,6 +269,7 @@ template <bool CKKS> Handle VectorBenchmarkT<CKKS>::operate(Handle h_remote_pack
         out.shard[g] = r;
         out.ids[g]   = std::move(sh.result);
     });
+    cw.prepareStore(out);         // host memory for store(), touched while the GPUs work
     cw.endOperate(out.n_total);   // waits for every GPU: the harness times this call by wall clock
     return this->getEngine().template createHandle<ShardedCiphertexts>(sizeof(ShardedCiphertexts), 0, std::move(out));
 }

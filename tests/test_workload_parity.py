@@ -46,7 +46,9 @@ GPUS = [None]   # HEB_B200_GPUS of the harness runs (None: the environment's / o
 
 
 def run_harness(plugin, args, trace_dir, picks=None, timeout=1500):
-    env = dict(os.environ, HEB_B200_TRACE_DIR=str(trace_dir), HEB_B200_SEED=str(SEED))
+    # HEB_B200_POPULATE_MIN_MB=0: the result arenas of store() (made and touched during operate(), for results of a gigabyte
+    # and more by default) are used at every size, so these tests cover that path
+    env = dict(os.environ, HEB_B200_TRACE_DIR=str(trace_dir), HEB_B200_SEED=str(SEED), HEB_B200_POPULATE_MIN_MB="0")
     if GPUS[0]:
         env["HEB_B200_GPUS"] = str(GPUS[0])
     for tag, ids in (picks or {}).items():
