@@ -151,19 +151,70 @@ struct MacArgs {
     size_t a_stride, b_stride, out_stride;   // words per ciphertext
     int L;
     u32 rows, inner, cols, tiles_j, ntiles;
-    u32 reduce_every;      // fold the accumulators after this many terms (host: floor(2^127 / max q^2), at least 1)
+    u32 reduce_every;      // fold the accumulators before a run passes this many terms (host: floor(2^127 / max q^2), at least 1)
+    u32 flush_every;       // integer-pipe limbs: steps of the k loop between flushes of MacAcc's odd part (host, from max q; at least 1)
 };
-// (hi:lo) += x * y
-__device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 x, u64 y)
-{
+// 128-bit accumulator of 64 x 64-bit products for the integer-pipe limbs of k_tensor_mac, laid out so that a product
+// costs exactly four IMAD.WIDE.U32 and no register moves: with x = x1 2^32 + x0,
+//   even part (w3..w0, 128 bits)  += x0 y0 + 2^64 x1 y1     two multiply-adds chained by the carry flag
+//   odd part  (o1:o0, weight 2^32) += x0 y1 + x1 y0          two multiply-adds, no carry word: the caller adds the odd
+//                                                            part into the even one (flush) before it can overflow --
+//                                                            every MacArgs::flush_every steps of the k loop
+// Every multiply-add reads and writes an aligned register pair.  (The obvious forms -- mad.lo.cc.u64 / madc.hi.u64, or
+// one schoolbook chain over four words -- cost ~20 and ~13 instructions per product in SASS: seven multiplies and
+// compare-and-select carries, or a register move per multiply because the middle words straddle two pairs.)
+struct MacAcc {
 #if defined(__CUDA_ARCH__)
-    asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\tmadc.hi.u64 %1, %2, %3, %1;" : "+l"(lo), "+l"(hi) : "l"(x), "l"(y));
-#else
-    const unsigned __int128 s = (((unsigned __int128)hi << 64) | lo) + (unsigned __int128)x * y;
-    lo = (u64)s;
-    hi = (u64)(s >> 64);
+    u64 elo, ehi, odd;   // 64-bit values: the register allocator keeps each in an aligned pair, which is what IMAD.WIDE wants
+    __device__ __forceinline__ void zero() { elo = ehi = odd = 0; }
+    __device__ __forceinline__ void mac(u64 x, u64 y)
+    {
+        const u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
+        asm("{\n\t"
+            ".reg .u64 p, q;\n\t"
+            "mul.wide.u32 p, %3, %5;\n\t"
+            "mul.wide.u32 q, %4, %6;\n\t"
+            "add.cc.u64 %0, %0, p;\n\t"
+            "addc.u64 %1, %1, q;\n\t"
+            "mad.wide.u32 %2, %3, %6, %2;\n\t"
+            "mad.wide.u32 %2, %4, %5, %2;\n\t"
+            "}"
+            : "+l"(elo), "+l"(ehi), "+l"(odd)
+            : "r"(x0), "r"(x1), "r"(y0), "r"(y1));
+    }
+    __device__ __forceinline__ void flush()
+    {
+        // (ehi:elo) += odd * 2^32
+        asm("{\n\t"
+            ".reg .u64 a, b;\n\t"
+            "shl.b64 a, %2, 32;\n\t"
+            "shr.u64 b, %2, 32;\n\t"
+            "add.cc.u64 %0, %0, a;\n\t"
+            "addc.u64 %1, %1, b;\n\t"
+            "}"
+            : "+l"(elo), "+l"(ehi)
+            : "l"(odd));
+        odd = 0;
+    }
+    __device__ __forceinline__ u64 lo() const { return elo; }
+    __device__ __forceinline__ u64 hi() const { return ehi; }
+    __device__ __forceinline__ void set(u64 l) { elo = l; ehi = 0; }
+#else   // the emulation build keeps the same two parts (and the same overflow behaviour of the odd one)
+    unsigned __int128 even;
+    u64 odd;
+    void zero() { even = 0; odd = 0; }
+    void mac(u64 x, u64 y)
+    {
+        const u64 x0 = (u32)x, x1 = x >> 32, y0 = (u32)y, y1 = y >> 32;
+        even += (unsigned __int128)(x0 * y0) + ((unsigned __int128)(x1 * y1) << 64);
+        odd += x0 * y1 + x1 * y0;
+    }
+    void flush() { even += (unsigned __int128)odd << 32; odd = 0; }
+    u64 lo() const { return (u64)even; }
+    u64 hi() const { return (u64)(even >> 64); }
+    void set(u64 l) { even = l; }
 #endif
-}
+};
 // any 128-bit value -> canonical residue: (hi mod q) * (2^64 mod q) + (lo mod q)
 __device__ __forceinline__ u64 fold128(u64 lo, u64 hi, const Mod &m, u64 r64q) { return mad_mod(reduce64(hi, m), r64q, reduce64(lo, m), m); }
 // FP64-domain instance (moduli below 2^46, modarith.cuh): a residue splits exactly into two halves below 2^23 held in
@@ -207,24 +258,27 @@ template <int TI, int TJ> __device__ __forceinline__ void tensor_mac_dp(const Ta
         for (int tj = 0; tj < TJ; tj++)
 #pragma unroll
             for (int c = 0; c < 3; c++) acc[ti][tj][c] = DpAcc{ 0.0, 0.0, 0.0 };
-    size_t ia[TI], jb[TJ];
+    const u64 *pa[TI], *pb[TJ];   // walk the inner dimension: one stride per step
 #pragma unroll
-    for (int ti = 0; ti < TI; ti++) ia[ti] = (size_t)(i0 + ti < A.rows ? i0 + ti : A.rows - 1) * A.inner;
+    for (int ti = 0; ti < TI; ti++) pa[ti] = A.a + (size_t)(i0 + ti < A.rows ? i0 + ti : A.rows - 1) * A.inner * A.a_stride + ce;
 #pragma unroll
-    for (int tj = 0; tj < TJ; tj++) jb[tj] = (size_t)(j0 + tj < A.cols ? j0 + tj : A.cols - 1) * A.inner;
+    for (int tj = 0; tj < TJ; tj++) pb[tj] = A.b + (size_t)(j0 + tj < A.cols ? j0 + tj : A.cols - 1) * A.inner * A.b_stride + ce;
+    // (requesting the operands of step k + 1 before the multiply-accumulates of step k was measured: 28.0 -> 30.9 ms on the
+    // 48 x 48 x 48 probe -- at 128 registers the second operand set costs more in moves and spills than the latency it hides)
     u32 run = 0;
+#pragma unroll 1
     for (u32 k = 0; k < A.inner; k++) {
         DpHalves a0[TI], a1[TI];
 #pragma unroll
         for (int ti = 0; ti < TI; ti++) {
-            const u64 *pa = A.a + (ia[ti] + k) * A.a_stride + ce;
-            a0[ti] = dp_split23(ldg1(pa));
-            a1[ti] = dp_split23(ldg1(pa + LN));
+            a0[ti] = dp_split23(ldg1(pa[ti]));
+            a1[ti] = dp_split23(ldg1(pa[ti] + LN));
+            pa[ti] += A.a_stride;
         }
 #pragma unroll
         for (int tj = 0; tj < TJ; tj++) {
-            const u64 *pb = A.b + (jb[tj] + k) * A.b_stride + ce;
-            const DpHalves b0 = dp_split23(ldg1(pb)), b1 = dp_split23(ldg1(pb + LN));
+            const DpHalves b0 = dp_split23(ldg1(pb[tj])), b1 = dp_split23(ldg1(pb[tj] + LN));
+            pb[tj] += A.b_stride;
 #pragma unroll
             for (int ti = 0; ti < TI; ti++) {
                 acc[ti][tj][0].mac(a0[ti], b0);
@@ -257,55 +311,59 @@ template <int TI, int TJ> __device__ __forceinline__ void tensor_mac_int(const T
 {
     const size_t LN = (size_t)A.L * T.N;
     const u64 r64q = reduce64(m.nq, m);   // 2^64 mod q
-    u64 lo[TI][TJ][3], hi[TI][TJ][3];
+    MacAcc acc[TI][TJ][3];
 #pragma unroll
     for (int ti = 0; ti < TI; ti++)
 #pragma unroll
         for (int tj = 0; tj < TJ; tj++)
 #pragma unroll
-            for (int c = 0; c < 3; c++) lo[ti][tj][c] = hi[ti][tj][c] = 0;
+            for (int c = 0; c < 3; c++) acc[ti][tj][c].zero();
     // rows / columns beyond the matrix (edge tiles) repeat the last valid one; their results are not stored
-    size_t ia[TI], jb[TJ];
+    const u64 *pa[TI], *pb[TJ];   // walk the inner dimension: one stride per step
 #pragma unroll
-    for (int ti = 0; ti < TI; ti++) ia[ti] = (size_t)(i0 + ti < A.rows ? i0 + ti : A.rows - 1) * A.inner;
+    for (int ti = 0; ti < TI; ti++) pa[ti] = A.a + (size_t)(i0 + ti < A.rows ? i0 + ti : A.rows - 1) * A.inner * A.a_stride + ce;
 #pragma unroll
-    for (int tj = 0; tj < TJ; tj++) jb[tj] = (size_t)(j0 + tj < A.cols ? j0 + tj : A.cols - 1) * A.inner;
+    for (int tj = 0; tj < TJ; tj++) pb[tj] = A.b + (size_t)(j0 + tj < A.cols ? j0 + tj : A.cols - 1) * A.inner * A.b_stride + ce;
     u32 run = 0;
-    for (u32 k = 0; k < A.inner; k++) {
-        u64 a0[TI], a1[TI], b0[TJ], b1[TJ];
+    for (u32 k = 0; k < A.inner;) {
+        const u32 kend = k + A.flush_every < A.inner ? k + A.flush_every : A.inner;
+#pragma unroll 1
+        for (; k < kend; k++) {
+            u64 a0[TI], a1[TI], b0[TJ], b1[TJ];
 #pragma unroll
-        for (int ti = 0; ti < TI; ti++) {
-            const u64 *pa = A.a + (ia[ti] + k) * A.a_stride + ce;
-            a0[ti] = ldg1(pa);
-            a1[ti] = ldg1(pa + LN);
-        }
-#pragma unroll
-        for (int tj = 0; tj < TJ; tj++) {
-            const u64 *pb = A.b + (jb[tj] + k) * A.b_stride + ce;
-            b0[tj] = ldg1(pb);
-            b1[tj] = ldg1(pb + LN);
-        }
-#pragma unroll
-        for (int ti = 0; ti < TI; ti++)
+            for (int ti = 0; ti < TI; ti++) {
+                a0[ti] = ldg1(pa[ti]);
+                a1[ti] = ldg1(pa[ti] + LN);
+                pa[ti] += A.a_stride;
+            }
 #pragma unroll
             for (int tj = 0; tj < TJ; tj++) {
-                mac128(lo[ti][tj][0], hi[ti][tj][0], a0[ti], b0[tj]);
-                mac128(lo[ti][tj][1], hi[ti][tj][1], a0[ti], b1[tj]);
-                mac128(lo[ti][tj][1], hi[ti][tj][1], a1[ti], b0[tj]);
-                mac128(lo[ti][tj][2], hi[ti][tj][2], a1[ti], b1[tj]);
+                b0[tj] = ldg1(pb[tj]);
+                b1[tj] = ldg1(pb[tj] + LN);
+                pb[tj] += A.b_stride;
             }
-        if (++run == A.reduce_every && k + 1 < A.inner) {
-            run = 0;
 #pragma unroll
             for (int ti = 0; ti < TI; ti++)
 #pragma unroll
-                for (int tj = 0; tj < TJ; tj++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        lo[ti][tj][c] = fold128(lo[ti][tj][c], hi[ti][tj][c], m, r64q);
-                        hi[ti][tj][c] = 0;
-                    }
+                for (int tj = 0; tj < TJ; tj++) {
+                    acc[ti][tj][0].mac(a0[ti], b0[tj]);
+                    acc[ti][tj][1].mac(a0[ti], b1[tj]);
+                    acc[ti][tj][1].mac(a1[ti], b0[tj]);
+                    acc[ti][tj][2].mac(a1[ti], b1[tj]);
+                }
         }
+        run += A.flush_every;
+        const bool fold = run + A.flush_every > A.reduce_every && k < A.inner;   // the next stretch would pass the 128-bit bound
+#pragma unroll
+        for (int ti = 0; ti < TI; ti++)
+#pragma unroll
+            for (int tj = 0; tj < TJ; tj++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    acc[ti][tj][c].flush();
+                    if (fold) acc[ti][tj][c].set(fold128(acc[ti][tj][c].lo(), acc[ti][tj][c].hi(), m, r64q));
+                }
+        if (fold) run = 0;
     }
 #pragma unroll
     for (int ti = 0; ti < TI; ti++)
@@ -314,7 +372,7 @@ template <int TI, int TJ> __device__ __forceinline__ void tensor_mac_int(const T
             if (i0 + ti >= A.rows || j0 + tj >= A.cols) continue;
             u64 *o = A.out + ((size_t)(i0 + ti) * A.cols + (j0 + tj)) * A.out_stride + ce;
 #pragma unroll
-            for (int c = 0; c < 3; c++) o[(size_t)c * LN] = fold128(lo[ti][tj][c], hi[ti][tj][c], m, r64q);
+            for (int c = 0; c < 3; c++) o[(size_t)c * LN] = fold128(acc[ti][tj][c].lo(), acc[ti][tj][c].hi(), m, r64q);
         }
 }
 // a block covers MAC_THREADS consecutive coefficients of one limb ([L][N], N a multiple of the block size): the modulus,
@@ -329,7 +387,14 @@ template <int TI, int TJ> __global__ void __launch_bounds__(B200HE_MAC_THREADS, 
     const Mod m = T.mods[ce / N];
     const u32 i0 = (tile / A.tiles_j) * TI, j0 = (tile % A.tiles_j) * TJ;
     if (m.dp) tensor_mac_dp<TI, TJ>(T, A, m, ce, i0, j0);
-    else tensor_mac_int<TI, TJ>(T, A, m, ce, i0, j0);
+    else {
+        // a 2 x 2 tile of MacAcc (12 x 6 words, next to 8 operands and 4 pointers) does not fit the 128 registers that
+        // four resident blocks allow -- the allocator answered with ~70 register moves per step -- so the rows of the
+        // tile are done one after the other; the second pass finds the b operands in L2
+#pragma unroll 1
+        for (int ti = 0; ti < TI; ti++)
+            if (i0 + ti < A.rows) tensor_mac_int<1, TJ>(T, A, m, ce, i0 + ti, j0);
+    }
 }
 
 // ------------------------------------------------------------------------------------ K8
