@@ -12,10 +12,12 @@
 //
 // CTA shape.  Every NTT-bearing kernel runs CTAs of N_loc/16 threads (512 for N >= 8192) that own a local transform of
 // N_loc = min(N, 8192) coefficients: 64 KiB of shared memory, 16 coefficients per thread in registers.  For N = 16384 /
-// 32768 a limb belongs to a thread-block CLUSTER of 2 / 4 CTAs; CTA r owns chunk r, and the 1-2 transform stages that
-// span chunks run as one radix-2/4 butterfly per offset on values exchanged through distributed shared memory
-// (cross_fwd / cross_inv below): no butterfly is computed twice, no second kernel finishes a split inverse, and a limb
-// crosses HBM exactly once per direction for every N.
+// 32768 a limb belongs to a group of 2 / 4 CTAs; CTA r owns chunk r.  In a cluster of 4 the two transform stages that
+// span chunks run as one radix-4 butterfly per offset on values exchanged through distributed shared memory (cross_fwd /
+// cross_inv below): no butterfly is computed twice and no second kernel finishes a split inverse.  A group of 2 does the
+// same for its inverse cross stage; in the forward direction each of the two CTAs reads its sibling's chunk from global
+// memory (L2) and computes the single cross stage for itself -- half a butterfly per coefficient costs less than the
+// DSMEM round trip and the two cluster barriers (load_fwd_split; measured).
 #pragma once
 #include "ntt_core.cuh"
 #ifndef B200HE_EMU
