@@ -31,10 +31,17 @@ struct Plaintext {
 class HostSlab
 {
 public:
-    static std::shared_ptr<HostSlab> create(std::size_t bytes);   // nullptr when the mapping cannot be made
+    // An arena of at least `bytes`: a recycled one when the pool holds a fitting mapping (already resident, no system call),
+    // a new mapping otherwise; nullptr when the mapping cannot be made.  The last owner hands the arena back to the pool
+    // instead of unmapping it: HEBench calls operate() again and again on the same shapes, and unmapping gigabytes (or
+    // touching them for the first time) next to a running operate() costs that call tens of milliseconds of address-space
+    // lock contention (measured at 2 GPUs: C3 operate() 127 -> 163 ms before the pool existed).
+    static std::shared_ptr<HostSlab> create(std::size_t bytes);
     // Make the arena's pages resident from a few background threads without changing their contents (so it may run
-    // while store() is already copying into the arena).  The threads stop when the last owner lets go of the arena.
+    // while store() is already copying into the arena); continues where an earlier call stopped.  The threads stop when
+    // the last owner lets go of the arena.
     static void populate(const std::shared_ptr<HostSlab> &slab, int threads);
+    static void trim();   // unmap everything the pool holds (benchmark teardown)
     std::size_t bytes() const { return m_bytes; }
     ~HostSlab();
     HostSlab(const HostSlab &) = delete;
@@ -49,11 +56,13 @@ public:
 
 private:
     HostSlab(void *map, std::size_t map_bytes, void *base, std::size_t bytes) : m_map(map), m_map_bytes(map_bytes), m_base(base), m_bytes(bytes) {}
+    static void recycle(HostSlab *slab);
     void *m_map;
     std::size_t m_map_bytes;
     void *m_base;
     std::size_t m_bytes;
     std::atomic<std::size_t> m_used{ 0 };
+    std::atomic<std::size_t> m_resident{ 0 };   // populate()'s progress: the next stripe to touch
 };
 // Allocator of Ciphertext::data.  (1) resize() leaves new words uninitialised: a result ciphertext is overwritten in
 // full by store(), and zero-filling gigabytes first costs as much as the copy itself.  (2) Optionally bound to a

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <sstream>
 #include <thread>
@@ -89,6 +90,7 @@ void SEALContextWrapper::init(bool ckks, std::size_t N, std::size_t depth, int c
 
 SEALContextWrapper::~SEALContextWrapper()
 {
+    HostSlab::trim();
     m_mask_cache.clear();
     for (b200he_ctx *c : m_dev) b200he_ctx_destroy(c);
     if (m_host) hfhe_destroy(m_host);
@@ -285,39 +287,86 @@ HostSlab::~HostSlab()
 {
     if (m_map) munmap(m_map, m_map_bytes);
 }
+namespace {
+std::mutex g_slab_mtx;
+std::vector<HostSlab *> g_slab_pool;
+std::size_t g_slab_pool_bytes = 0;
+std::size_t slabPoolCap()
+{
+    std::size_t mb = 32768;   // arenas kept for reuse, in total
+    if (const char *e = std::getenv("HEB_B200_HOST_POOL_MB")) mb = (std::size_t)std::atoll(e);
+    return mb << 20;
+}
+}   // namespace
+void HostSlab::recycle(HostSlab *slab)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_slab_mtx);
+        if (g_slab_pool_bytes + slab->m_bytes <= slabPoolCap()) {
+            g_slab_pool.push_back(slab);
+            g_slab_pool_bytes += slab->m_bytes;
+            return;
+        }
+    }
+    delete slab;
+}
+void HostSlab::trim()
+{
+    std::vector<HostSlab *> all;
+    {
+        std::lock_guard<std::mutex> lock(g_slab_mtx);
+        all.swap(g_slab_pool);
+        g_slab_pool_bytes = 0;
+    }
+    for (HostSlab *s : all) delete s;
+}
 std::shared_ptr<HostSlab> HostSlab::create(std::size_t bytes)
 {
     const std::size_t huge = std::size_t(2) << 20;
     if (!bytes) return nullptr;
     if (const char *e = std::getenv("HEB_B200_HOST_SLAB"))
         if (std::atoi(e) == 0) return nullptr;
+    {   // smallest pooled arena that fits without wasting more than half of itself
+        std::lock_guard<std::mutex> lock(g_slab_mtx);
+        std::size_t best = g_slab_pool.size();
+        for (std::size_t i = 0; i < g_slab_pool.size(); ++i) {
+            const std::size_t have = g_slab_pool[i]->m_bytes;
+            if (have >= bytes && have / 2 <= bytes && (best == g_slab_pool.size() || have < g_slab_pool[best]->m_bytes)) best = i;
+        }
+        if (best != g_slab_pool.size()) {
+            HostSlab *slab = g_slab_pool[best];
+            g_slab_pool.erase(g_slab_pool.begin() + (std::ptrdiff_t)best);
+            g_slab_pool_bytes -= slab->m_bytes;
+            slab->m_used.store(0, std::memory_order_relaxed);
+            return std::shared_ptr<HostSlab>(slab, &HostSlab::recycle);
+        }
+    }
     const std::size_t span = ((bytes + huge - 1) & ~(huge - 1)) + huge;
     void *map              = mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (map == MAP_FAILED) return nullptr;
     void *base = reinterpret_cast<void *>((reinterpret_cast<std::uintptr_t>(map) + huge - 1) & ~std::uintptr_t(huge - 1));
     madvise(base, span - huge, MADV_HUGEPAGE);   // advisory: 4 KB pages where transparent huge pages are off
-    return std::shared_ptr<HostSlab>(new HostSlab(map, span, base, span - huge));
+    return std::shared_ptr<HostSlab>(new HostSlab(map, span, base, span - huge), &HostSlab::recycle);
 }
 
 void HostSlab::populate(const std::shared_ptr<HostSlab> &slab, int threads)
 {
-    if (!slab || threads < 1) return;
-    // short stripes: a populate call holds the address space's lock shared, and anything on the other threads that needs
-    // it exclusively (an mmap inside malloc or the driver) waits for the stripes in flight
+    if (!slab || threads < 1 || slab->m_resident.load(std::memory_order_relaxed) >= slab->m_bytes) return;
+    // Pages are made resident by touching them (an atomic OR of 0: the byte keeps its value, so store() may already be
+    // copying into the arena).  MADV_POPULATE_WRITE does the same in one call per stripe but holds the address space's lock
+    // shared for the whole stripe, and everything that needs it exclusively -- thread creation, the driver's and malloc's
+    // mmap calls inside operate() -- queues behind it: measured at 2 GPUs, operate() calls overlapping such a populate ran
+    // 168 / 135 ms instead of 120.5 ms; page faults take the per-VMA lock and leave them alone (120.6 ms).
     const std::size_t stripe = std::size_t(4) << 20;
-    std::shared_ptr<std::atomic<std::size_t>> next = std::make_shared<std::atomic<std::size_t>>(0);
     for (int t = 0; t < threads; ++t) {
         std::weak_ptr<HostSlab> weak = slab;
-        std::thread([weak, next, stripe]() {
+        std::thread([weak, stripe]() {
             while (std::shared_ptr<HostSlab> s = weak.lock()) {   // held for one stripe at a time
-                const std::size_t at = next->fetch_add(stripe, std::memory_order_relaxed);
+                const std::size_t at = s->m_resident.fetch_add(stripe, std::memory_order_relaxed);
                 if (at >= s->m_bytes) return;
                 char *p               = static_cast<char *>(s->m_base) + at;
                 const std::size_t len = std::min(stripe, s->m_bytes - at);
-#ifdef MADV_POPULATE_WRITE
-                if (madvise(p, len, MADV_POPULATE_WRITE) == 0) continue;
-#endif
-                for (std::size_t o = 0; o < len; o += 4096) __atomic_fetch_or(p + o, 0, __ATOMIC_RELAXED);   // touches, keeps the byte
+                for (std::size_t o = 0; o < len; o += 4096) __atomic_fetch_or(p + o, 0, __ATOMIC_RELAXED);
             }
         }).detach();
     }
