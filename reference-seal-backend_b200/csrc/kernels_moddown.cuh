@@ -28,7 +28,7 @@ struct ModDownArgs {
     size_t rp_raw_stride;
     const u64 *base;       // base + b*base_ct_stride + p*base_poly_stride + j*N
     size_t base_ct_stride, base_poly_stride;
-    const u64 *addend[2];  // per poly (P <= 2 when addend used) or nullptr; addend[p] + b*add_ct_stride + j*N
+    const u64 *addend[3];  // per poly (a ciphertext has at most 3) or nullptr; addend[p] + b*add_ct_stride + j*N
     size_t add_ct_stride;
     u64 *out;              // out + b*out_ct_stride + p*out_poly_stride + j*N
     size_t out_ct_stride, out_poly_stride;

@@ -19,6 +19,8 @@ def emu_lib():
     """the product's CUDA sources compiled as host C++ (tests/emu): checks kernel index arithmetic on CPU"""
     import ctypes
     import pyb200he
+    if os.environ.get("B200HE_EMU_LIB"):   # e.g. an AddressSanitizer build of the same sources (tests/emu/build_emu_asan.sh)
+        return pyb200he.declare(ctypes.CDLL(os.environ["B200HE_EMU_LIB"]))
     so = os.path.join(ROOT, "tests", "emu", "libb200he_emu.so")
     srcs = [os.path.join(ROOT, "reference-seal-backend_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "reference-seal-backend_b200", "csrc"))]
     srcs += [os.path.join(ROOT, "tests", "emu", f) for f in ("cuda_shim.cpp", "cuda_shim.h")]

@@ -164,6 +164,8 @@ def check_logreg(plugin, tmp, N, depth, degree, batch, n_features=16):
 # ------------------------------------------------------------------------------------------- CPU: emulation plugin
 @pytest.fixture(scope="module")
 def emu_plugin(emu_lib):
+    if os.environ.get("B200HE_EMU_PLUGIN"):   # a sanitizer build of the plugin (tests/emu/run_asan.sh)
+        return os.environ["B200HE_EMU_PLUGIN"]
     import __graft_entry__ as g
     g.build_host()
     subprocess.check_call(["make", "-s", "-C", BACKEND, "emu"])
