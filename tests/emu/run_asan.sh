@@ -26,7 +26,9 @@ make -s -C "$root/reference-seal-backend_b200/hostfhe" >/dev/null 2>&1 || true
 g++ -fsanitize=address,undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer -g -O1 -std=c++17 -fPIC -fopenmp -I"$back/compat" -I"$back/include" -I"$root/include" \
     -shared -o "$obj/libhebench_seal_backend_emu_asan.so" "$back"/src/engine/*.cpp "$back"/src/benchmarks/*.cpp "$back/compat/hebench/api_bridge/cpp/hebench_cpp.cpp" \
     -L"$obj" -lb200he_emu_asan -L"$root/reference-seal-backend_b200/hostfhe" -lhostfhe -Wl,-rpath,"$obj" -Wl,-rpath,"$root/reference-seal-backend_b200/hostfhe"
+# the CPU oracle (the checker itself) with the same sanitizers
+g++ -fsanitize=address,undefined -fno-sanitize-recover=undefined -g -O1 -fopenmp -fPIC -std=c++17 -shared -o "$obj/libhe_oracle_asan.so" "$root/oracle/he_oracle.cpp" "$root/oracle/he_oracle_workloads.cpp"
 cd "$root"
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
 ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
-B200HE_EMU_LIB="$obj/libb200he_emu_asan.so" B200HE_EMU_PLUGIN="$obj/libhebench_seal_backend_emu_asan.so" python -m pytest tests/test_emu_parity.py tests/test_workload_parity.py -m "not gpu" -x -q "$@"
+B200HE_EMU_LIB="$obj/libb200he_emu_asan.so" B200HE_EMU_PLUGIN="$obj/libhebench_seal_backend_emu_asan.so" B200HE_ORACLE_LIB="$obj/libhe_oracle_asan.so" python -m pytest tests/test_oracle.py tests/test_emu_parity.py tests/test_workload_parity.py -m "not gpu" -x -q "$@"

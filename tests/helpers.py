@@ -26,7 +26,7 @@ _oracle = None
 def oracle():
     global _oracle
     if _oracle is None:
-        path = os.path.join(ROOT, "oracle", "libhe_oracle.so")
+        path = os.environ.get("B200HE_ORACLE_LIB") or os.path.join(ROOT, "oracle", "libhe_oracle.so")   # (a sanitizer build, tests/emu/run_asan.sh)
         if not os.path.exists(path):
             import subprocess
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
