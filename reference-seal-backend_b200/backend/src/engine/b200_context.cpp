@@ -288,9 +288,11 @@ HostSlab::~HostSlab()
     if (m_map) munmap(m_map, m_map_bytes);
 }
 namespace {
-std::mutex g_slab_mtx;
-std::vector<HostSlab *> g_slab_pool;
-std::size_t g_slab_pool_bytes = 0;
+// never destroyed: a background populate thread may hand an arena back while the process is already running its static
+// destructors
+std::mutex &g_slab_mtx                = *new std::mutex;
+std::vector<HostSlab *> &g_slab_pool = *new std::vector<HostSlab *>;
+std::size_t g_slab_pool_bytes         = 0;
 std::size_t slabPoolCap()
 {
     std::size_t mb = 32768;   // arenas kept for reuse, in total
