@@ -7,6 +7,8 @@
 //
 //   mini_harness --backend_lib_path libhebench_seal_backend.so [--random_seed 1234] [--filter TEXT] [--list]
 //                [--samples A,B] [--batch N] [--iterations K] [--n N] [--dims R,C0,C1] [--poly N] [--depth D] [--csv FILE]
+//                [--sub V0,B0,V1,B1]    element-wise / dot product: operate() on that index range of the loaded samples (ParameterIndexer)
+//                [--expect-operate-error]   the run passes when operate() rejects the request
 //                [--json FILE]          one JSON object per benchmark: wall time of every phase (encode ... decode), every timed operate()
 //                [--extra-operate K]    K more untimed operate() calls after the timed ones (the backend profiles those, HEB_B200_PROFILE_*)
 #include <dlfcn.h>
@@ -34,6 +36,8 @@ struct Options {
     unsigned seed = 1234;
     bool list = false;
     uint64_t samples[2] = { 2, 3 }, batch = 8, iterations = 2, n = 0, dims[3] = { 0, 0, 0 }, poly = 0, depth = 0, extra_operate = 0;
+    uint64_t sub[4] = { 0, 0, 0, 0 };   // --sub v0,b0,v1,b1: operate() on the index range [v0, v0+b0) x [v1, v1+b1) of the loaded samples
+    bool have_sub = false, expect_operate_error = false;
 };
 
 static const char *workloadName(Workload w)
@@ -101,6 +105,8 @@ int main(int argc, char **argv)
         else if (a == "--extra-operate") o.extra_operate = strtoull(next().c_str(), nullptr, 10);
         else if (a == "--list") o.list = true;
         else if (a == "--samples") sscanf(next().c_str(), "%lu,%lu", &o.samples[0], &o.samples[1]);
+        else if (a == "--sub") { sscanf(next().c_str(), "%lu,%lu,%lu,%lu", &o.sub[0], &o.sub[1], &o.sub[2], &o.sub[3]); o.have_sub = true; }
+        else if (a == "--expect-operate-error") o.expect_operate_error = true;
         else if (a == "--batch") o.batch = strtoull(next().c_str(), nullptr, 10);
         else if (a == "--iterations") o.iterations = strtoull(next().c_str(), nullptr, 10);
         else if (a == "--n") o.n = strtoull(next().c_str(), nullptr, 10);
@@ -204,9 +210,12 @@ int main(int argc, char **argv)
             in.bytes[1].resize(s1);
             for (auto &b : in.bytes[0]) fill(b, n);
             for (auto &b : in.bytes[1]) fill(b, n);
-            results = s0 * s1;
-            for (uint64_t i = 0; i < s0; ++i)
-                for (uint64_t j = 0; j < s1; ++j) {
+            // ParameterIndexer sub-ranges (R/src/benchmarks/ckks/seal_ckks_element_wise_benchmark.cpp:334-336): results are
+            // ordered (i - v0) * b1 + (j - v1)
+            const uint64_t v0 = o.have_sub ? o.sub[0] : 0, b0 = o.have_sub ? o.sub[1] : s0, v1 = o.have_sub ? o.sub[2] : 0, b1 = o.have_sub ? o.sub[3] : s1;
+            results = b0 * b1;
+            for (uint64_t i = v0; i < v0 + b0 && i < s0; ++i)
+                for (uint64_t j = v1; j < v1 + b1 && j < s1; ++j) {
                     std::vector<double> t;
                     if (bd.workload == DotProduct) {
                         double acc = 0;
@@ -217,7 +226,7 @@ int main(int argc, char **argv)
                             t.push_back(bd.workload == EltwiseAdd ? val(in.bytes[0][i], k) + val(in.bytes[1][j], k) : val(in.bytes[0][i], k) * val(in.bytes[1][j], k));
                     truth.push_back(t);
                 }
-            idx = { { 0, s0 }, { 0, s1 } };
+            idx = { { v0, b0 }, { v1, b1 } };
         } else if (is_mat) {
             const uint64_t r0 = wp[0].u_param, c0 = wp[1].u_param, c1 = wp[2].u_param;
             in.bytes.resize(2);
@@ -260,7 +269,7 @@ int main(int argc, char **argv)
             return std::chrono::duration<double, std::milli>(b - a).count();
         };
         Handle h_enc{}, h_cipher{}, h_remote{}, h_result{}, h_local{}, h_plain{};
-        bool ok = true;
+        bool ok = true, rejected = false;
         double t_load = 0, t_op = 0, t_store = 0, t_encode = 0, t_encrypt = 0, t_decrypt = 0, t_decode = 0, t_warm = 0;
         std::vector<double> t_ops;
         do {
@@ -274,7 +283,14 @@ int main(int argc, char **argv)
             if (p_load(bench, &h_cipher, 1, &h_remote)) { ok = false; break; }
             auto t1 = std::chrono::steady_clock::now();
             t_load  = ms(t0, t1);
-            if (p_operate(bench, h_remote, idx.data(), idx.size(), &h_result)) { ok = false; break; }   // warm-up
+            if (const int rc = p_operate(bench, h_remote, idx.data(), idx.size(), &h_result)) {   // warm-up
+                if (o.expect_operate_error) {
+                    printf("[ Info    ]     operate() rejected the indexers as expected: code %d, %s\n", rc, lastError().c_str());
+                    rejected = true;
+                }
+                ok = false;
+                break;
+            }
             t_warm = ms(t1, std::chrono::steady_clock::now());
             for (uint64_t it = 0; it < o.iterations; ++it) {
                 p_destroyHandle(h_result);
@@ -300,7 +316,12 @@ int main(int argc, char **argv)
             t_decode  = ms(t4, std::chrono::steady_clock::now());
         } while (false);
         uint64_t bad = 0;
-        if (!ok) {
+        if (o.expect_operate_error) {
+            if (!rejected) {
+                printf("[ Error   ] operate() accepted indexers it had to reject\n");
+                bad = 1;
+            }
+        } else if (!ok) {
             printf("[ Error   ] %s\n", lastError().c_str());
             bad = 1;
         } else {

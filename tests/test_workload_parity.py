@@ -78,19 +78,24 @@ def eq(got, want, what):
 
 
 # ------------------------------------------------------------------------------------------- per-workload checkers
-def check_vector(plugin, tmp, scheme, op, N, depth, coeff_bits, sp_bits, n, s0, s1, pick_out=None):
+def check_vector(plugin, tmp, scheme, op, N, depth, coeff_bits, sp_bits, n, s0, s1, pick_out=None, sub=None):
+    """sub = (v0, b0, v1, b1): operate() on the ParameterIndexer range [v0, v0+b0) x [v1, v1+b1) of the loaded samples
+    (R/src/benchmarks/ckks/seal_ckks_element_wise_benchmark.cpp:334-336); result r is sample pair (v0 + r // b1, v1 + r % b1)"""
     name = {"add": "EltwiseAdd", "mul": "EltwiseMultiply", "dot": "DotProduct"}[op]
     args = ["--filter", f"{name} {'CKKS' if scheme == CKKS else 'BFV'} Offline", "--n", str(n), "--samples", f"{s0},{s1}", "--poly", str(N), "--depth", str(depth)]
+    v0, b0, v1, b1 = sub if sub else (0, s0, 0, s1)
+    if sub:
+        args += ["--sub", ",".join(str(v) for v in sub)]
     run_harness(plugin, args, tmp, {"out": pick_out} if pick_out else None)
     k = Keys(scheme, N, depth, coeff_bits, sp_bits, galois=(op == "dot"))
     a, _, _ = read_trace(tmp, "in0")
     b, _, _ = read_trace(tmp, "in1")
     out, _, total = read_trace(tmp, "out")
-    assert a.shape[0] == s0 and b.shape[0] == s1 and total == s0 * s1
-    cells = list(pick_out) if pick_out else list(range(s0 * s1))
+    assert a.shape[0] == s0 and b.shape[0] == s1 and total == b0 * b1
+    cells = list(pick_out) if pick_out else list(range(b0 * b1))
     L = depth
     for r, cell in enumerate(cells):
-        x, y = a[cell // s1].reshape(-1), b[cell % s1].reshape(-1)
+        x, y = a[v0 + cell // b1].reshape(-1), b[v1 + cell % b1].reshape(-1)
         if op == "add":
             want = k.orc.add(L, 2, x, y)
         elif op == "mul":
@@ -180,6 +185,29 @@ def test_emu_vector_workloads(emu_plugin, tmp_path):
     check_vector(emu_plugin, tmp_path, BFV, "dot", 2048, 2, 45, 20, n=9, s0=1, s1=2)
 
 
+def test_emu_parameter_indexers(emu_plugin, tmp_path):
+    """operate() honours ParameterIndexer sub-ranges for the element-wise and dot-product workloads (result order
+    (i - v0) * b1 + (j - v1)), on one GPU and with the result space split over several, and rejects ranges that leave the
+    loaded samples; the matrix and logistic-regression workloads accept the full range only
+    (R/src/benchmarks/ckks/seal_ckks_element_wise_benchmark.cpp:321-336, ...matmultval...:451-461, ...logreg_horner.cpp:413-419)"""
+    check_vector(emu_plugin, tmp_path, CKKS, "mul", 2048, 2, 45, 45, n=16, s0=4, s1=3, sub=(1, 2, 1, 2))
+    check_vector(emu_plugin, tmp_path, CKKS, "dot", 2048, 2, 40, 40, n=10, s0=3, s1=5, sub=(2, 1, 1, 3))
+    check_vector(emu_plugin, tmp_path, BFV, "mul", 2048, 2, 40, 20, n=16, s0=3, s1=2, sub=(0, 3, 1, 1))
+    GPUS[0] = 3
+    try:
+        check_vector(emu_plugin, tmp_path, CKKS, "add", 2048, 2, 45, 45, n=16, s0=5, s1=2, sub=(1, 3, 0, 2))   # range spans two GPUs' blocks
+        check_vector(emu_plugin, tmp_path, CKKS, "dot", 2048, 2, 40, 40, n=10, s0=2, s1=7, sub=(0, 2, 3, 3))   # parameter 1 split
+    finally:
+        GPUS[0] = 0
+    base = ["--backend_lib_path", emu_plugin, "--iterations", "1", "--expect-operate-error", "--poly", "2048", "--depth", "2"]
+    env = dict(os.environ, HEB_B200_SEED=str(SEED))
+    for extra in (["--filter", "EltwiseAdd CKKS Offline", "--n", "8", "--samples", "3,2", "--sub", "2,2,0,2"],     # 2 + 2 > 3
+                  ["--filter", "DotProduct CKKS Offline", "--n", "8", "--samples", "2,2", "--sub", "0,2,1,2"]):    # 1 + 2 > 2
+        p = subprocess.run([HARNESS] + base + extra, capture_output=True, text=True, env=env, timeout=600)
+        assert "rejected the indexers as expected" in p.stdout and "Failed: 0" in p.stdout, p.stdout[-2000:] + p.stderr[-1000:]
+        assert "Invalid parameter indexer" in p.stdout, p.stdout[-2000:]
+
+
 @pytest.mark.parametrize("scheme", [CKKS, BFV], ids=["ckks", "bfv"])
 def test_emu_matmul_workloads(emu_plugin, tmp_path, scheme):
     bits = (45, 45) if scheme == CKKS else (40, 20)
@@ -226,6 +254,13 @@ def test_gpu_vector_workloads(plugin, tmp_path):
     check_vector(plugin, tmp_path, CKKS, "mul", 8192, 2, 45, 45, n=1000, s0=4, s1=3)
     check_vector(plugin, tmp_path, CKKS, "dot", 16384, 2, 40, 40, n=100, s0=3, s1=2)
     check_vector(plugin, tmp_path, BFV, "dot", 8192, 2, 45, 20, n=100, s0=2, s1=2)
+
+
+@pytest.mark.gpu
+def test_gpu_parameter_indexers(plugin, tmp_path):
+    """ParameterIndexer sub-ranges through the CUDA path: the C2 and C3 parameter sets on a window of the loaded samples"""
+    check_vector(plugin, tmp_path, CKKS, "mul", 8192, 2, 45, 45, n=1000, s0=5, s1=4, sub=(1, 3, 2, 2))
+    check_vector(plugin, tmp_path, CKKS, "dot", 16384, 2, 40, 40, n=100, s0=3, s1=4, sub=(2, 1, 1, 2))
 
 
 @pytest.mark.gpu
