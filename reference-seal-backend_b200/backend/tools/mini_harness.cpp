@@ -241,6 +241,7 @@ int main(int argc, char **argv)
             truth.push_back(t);
             results = 1;
             idx = { { 0, 1 }, { 0, 1 } };
+            if (o.have_sub) idx = { { o.sub[0], o.sub[1] }, { o.sub[2], o.sub[3] } };   // only to see it rejected (--expect-operate-error)
         } else {   // logistic regression
             const uint64_t n = wp[0].u_param;
             in.bytes.resize(3);
@@ -257,6 +258,7 @@ int main(int argc, char **argv)
             }
             results = batch;
             idx = { { 0, 1 }, { 0, 1 }, { 0, batch } };
+            if (o.have_sub) idx[2] = { o.sub[0], o.sub[1] };   // only to see it rejected (--expect-operate-error)
         }
         in.build();
         out.bytes.resize(1);

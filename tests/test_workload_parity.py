@@ -201,11 +201,15 @@ def test_emu_parameter_indexers(emu_plugin, tmp_path):
         GPUS[0] = 0
     base = ["--backend_lib_path", emu_plugin, "--iterations", "1", "--expect-operate-error", "--poly", "2048", "--depth", "2"]
     env = dict(os.environ, HEB_B200_SEED=str(SEED))
-    for extra in (["--filter", "EltwiseAdd CKKS Offline", "--n", "8", "--samples", "3,2", "--sub", "2,2,0,2"],     # 2 + 2 > 3
-                  ["--filter", "DotProduct CKKS Offline", "--n", "8", "--samples", "2,2", "--sub", "0,2,1,2"]):    # 1 + 2 > 2
-        p = subprocess.run([HARNESS] + base + extra, capture_output=True, text=True, env=env, timeout=600)
+    for extra, message in (
+            (["--filter", "EltwiseAdd CKKS Offline", "--n", "8", "--samples", "3,2", "--sub", "2,2,0,2"], "Invalid parameter indexer"),     # 2 + 2 > 3
+            (["--filter", "DotProduct CKKS Offline", "--n", "8", "--samples", "2,2", "--sub", "0,2,1,2"], "Invalid parameter indexer"),     # 1 + 2 > 2
+            (["--filter", "MatrixMultiply CKKS Latency other=0", "--dims", "2,3,2", "--sub", "1,1,0,1"], "Unexpected index"),              # value_index > 0
+            (["--filter", "MatrixMultiply CKKS Latency other=1", "--dims", "2,3,2", "--depth", "3", "--sub", "0,2,0,1"], "Batch size"),      # batch_size > 1
+            (["--filter", "LogisticRegression_PolyD3 CKKS Offline", "--batch", "4", "--depth", "6", "--sub", "1,3,0,0"], "indexer")):        # not the whole batch
+        p = subprocess.run([HARNESS] + base[:-2] + extra + ([] if "--depth" in extra else ["--depth", "2"]), capture_output=True, text=True, env=env, timeout=600)
         assert "rejected the indexers as expected" in p.stdout and "Failed: 0" in p.stdout, p.stdout[-2000:] + p.stderr[-1000:]
-        assert "Invalid parameter indexer" in p.stdout, p.stdout[-2000:]
+        assert message in p.stdout, p.stdout[-2000:]
 
 
 @pytest.mark.parametrize("scheme", [CKKS, BFV], ids=["ckks", "bfv"])
