@@ -616,7 +616,8 @@ def cpu_baseline(budget_s=12.0):
     probe = 4 * threads
     dt = cpu_sample(np, host, orc, probe, threads)
     n = int(max(probe, min(BATCH, probe * budget_s / max(dt, 1e-6))))
-    dt = cpu_sample(np, host, orc, n, threads)
+    cpu_sample(np, host, orc, n, threads)   # warm-up at the measured size (first touch of the result arrays, OpenMP team start):
+    dt = cpu_sample(np, host, orc, n, threads)   # without it this figure came out at half of what `--impl reference` measures
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} of the {BATCH} ciphertext pairs of one step, {threads} OpenMP threads over the batch like the reference's operate(); "
                       "SEAL-restatement oracle (SEAL itself is not buildable offline)"}
