@@ -256,6 +256,40 @@ __device__ __forceinline__ void cross_fwd(u64 (&x)[16], u64 *sm, int c, int r, i
     cross_collect<LOGN>(x, sm, c, r, tid);
 }
 
+// ONE Cooley-Tukey cross stage exchanged inside a cluster of TWO: `lo` = which chunk of the pair this CTA holds (its cluster
+// rank), w = the stage's twiddle.  Used by the forward-only kernels for limbs of four chunks (load_fwd_split, PAIRS): the
+// stage that pairs chunk r with r ^ 2 is computed from global memory, this one pairs r with r ^ 1.  Clusters of two fill
+// all 148 SMs; clusters of four only 132 (tools/cluster_occupancy.cu).
+// CTA `lo` owns register pairs [4 lo, 4 lo + 4): all four peer values are requested before the first is used, the own
+// operands are selected from the two candidate register groups so that no register index depends on lo.
+template <int LOGN, class Hook = NoHook>
+__device__ __forceinline__ void cross_fwd_pair(u64 (&x)[16], u64 *sm, int lo, int tid, ulonglong2 w, const Mod &m, Hook &&hook = Hook())
+{
+    typedef Pass<LOGN, 0> G0;
+    cross_publish<LOGN>(x, sm, 1, lo, tid);
+    cluster_sync();
+    {
+        u64 *peer = cluster_peer(sm, lo ^ 1);
+        ulonglong2 pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) pv[i] = ld2(peer + swz(G0::elem(tid, 4 * lo + i, 0)));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u64 o0 = lo ? x[8 + 2 * i] : x[2 * i], o1 = lo ? x[9 + 2 * i] : x[2 * i + 1];
+            u64 a0 = lo ? pv[i].x : o0, a1 = lo ? pv[i].y : o1;   // lower chunk of the pair
+            u64 b0 = lo ? o0 : pv[i].x, b1 = lo ? o1 : pv[i].y;   // upper chunk
+            ct_lazy(a0, b0, w, m);
+            ct_lazy(a1, b1, w, m);
+            st2(peer + swz(G0::elem(tid, 4 * lo + i, 0)), lo ? a0 : b0, lo ? a1 : b1);
+            if (lo) { x[8 + 2 * i] = b0; x[9 + 2 * i] = b1; }
+            else { x[2 * i] = a0; x[2 * i + 1] = a1; }
+        }
+    }
+    hook();
+    cluster_sync();
+    cross_collect<LOGN>(x, sm, 1, lo, tid);
+}
+
 // final cross-chunk stage of the inverse: (a + b) N^{-1} and (a - b) wn, results in [0, 2q) as integers (either domain)
 __device__ __forceinline__ void inv_last(u64 a, u64 b, ulonglong2 wn, const Mod &m, u64 &s, u64 &d)
 {
@@ -354,7 +388,9 @@ __device__ __forceinline__ void cross_inv(u64 (&x)[16], u64 *sm, int c, int r, i
 // input transform, and run the c cross-chunk stages.  pre.pair() must return values < 2q; the result is < (2 + 2c) q
 // (Mod::dp moduli: converted to the FP64 domain right after the load).
 // REUSE: the CTA has used the transform buffer before (see ntt_fwd_regs_split).
-template <int LOGN, bool REUSE = false, class Pre, class Hook = NoHook>
+// PAIRS: the kernel was launched with clusters of TWO although the limb has four chunks (forward-only kernels): the first
+// cross stage comes from global memory as for c == 1, the second is exchanged inside the pair (cross_fwd_pair).
+template <int LOGN, bool REUSE = false, bool PAIRS = false, class Pre, class Hook = NoHook>
 __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restrict__ src, int c, int r, int tid,
                                                const ulonglong2 *__restrict__ tw, const Mod &m, Pre pre, u64 *sm, Hook &&hook = Hook())
 {
@@ -391,6 +427,26 @@ __device__ __forceinline__ void load_fwd_split(u64 (&x)[16], const u64 *__restri
             x[reg + 1] = r ? b1 : a1;
         });
         hook();
+        return;
+    }
+    if (PAIRS && c == 2) {
+        const int hi = r >> 1;   // this chunk is the upper one of the stage that pairs r with r ^ 2
+        const size_t offp = (size_t)(r ^ 2) * NL;
+        const ulonglong2 w = ld_tw(tw + 1);
+        for_pairs_strided<LOGN>(tid, [&](int reg, int e) {
+            ulonglong2 p = pre.pair(ldg2(src + offp + e), offp + e);
+            if constexpr (!Pre::gives_dp) {
+                if (m.dp) { p.x = as_u(dp_from(p.x)); p.y = as_u(dp_from(p.y)); }
+            }
+            u64 a0 = hi ? p.x : x[reg], a1 = hi ? p.y : x[reg + 1];
+            u64 b0 = hi ? x[reg] : p.x, b1 = hi ? x[reg + 1] : p.y;
+            ct_lazy(a0, b0, w, m);
+            ct_lazy(a1, b1, w, m);
+            x[reg] = hi ? b0 : a0;
+            x[reg + 1] = hi ? b1 : a1;
+        });
+        if (REUSE) __syncthreads();
+        cross_fwd_pair<LOGN>(x, sm, r & 1, tid, ld_tw(tw + 2 + hi), m, hook);
         return;
     }
     if (c > 0) {

@@ -34,6 +34,7 @@ struct KsInnerArgs {
     // tile instead of two and owns no pre-processing.  fuse_add + b * ct_stride + k * poly_stride + (L-1) N, or nullptr.
     const u64 *fuse_add;
     size_t fuse_ct_stride, fuse_poly_stride;
+    int unit0;             // first unit of this launch (limbs of four chunks run as two launches: the special-prime units, then the rest)
 };
 // lazy accumulator of the inner product (either domain) -> canonical residue
 __device__ __forceinline__ u64 acc_finish(u64 a, const Mod &m) { return m.dp ? dp_canon(as_d(a), m) : reduce_full(a, m); }
@@ -43,7 +44,7 @@ template <int LOGN> struct KsCfg {
 // DP = Mod::dp of the CTA's modulus as a compile-time constant: the kernel branches once, at the top, into one of two
 // complete instances of the body, so the integer and the FP64-domain code never share live ranges (with the branch
 // inside the multiply-accumulate loop the register allocator spilled in both).
-template <int LOGN, int C, bool DP>
+template <int LOGN, int C, bool DP, bool PAIRS>
 __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs &A, Mod m, int b, int I, int ki, int r)
 {
     constexpr int c = C;
@@ -95,8 +96,8 @@ __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs
             auto load_t0 = [&]() { load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r); };
             if constexpr (C == 0) load_t0();
             auto split = [&](auto pre) {
-                if constexpr (C == 0) load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, pre, sm);
-                else load_fwd_split<LOGN, true>(x, tp, c, r, tid, tw, m, pre, sm, load_t0);
+                if constexpr (C == 0) load_fwd_split<LOGN, true, false>(x, tp, c, r, tid, tw, m, pre, sm);
+                else load_fwd_split<LOGN, true, PAIRS>(x, tp, c, r, tid, tw, m, pre, sm, load_t0);
             };
             if constexpr (DP) {   // FP64 domain: digits of moduli up to 48 bits are lazy values as they are (2^48 + 14 q < 2^50)
                 if (T.mods[J].bits > 48) split(PreLiftDp{ 1073741824.0 * m.dqinv, m.dnq });
@@ -221,18 +222,21 @@ __device__ __forceinline__ void ks_inner_body(const Tables &T, const KsInnerArgs
         warp_sync();   // the slice is rewritten by the next component
     }
 }
-template <int LOGN, int C>
+// PAIRS (limbs of four chunks only): the launch holds no special-prime unit, hence no inverse transform, and runs in clusters
+// of TWO -- the first cross stage from global memory, the second exchanged inside the pair (load_fwd_split) -- which fill all
+// 148 SMs where clusters of four fill 132.  The special-prime units keep their clusters of four in a launch of their own.
+template <int LOGN, int C, bool PAIRS = false>
 __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS, 1) k_ks_inner(Tables T, KsInnerArgs A)
 {
     const int r = blockIdx.x & ((1 << C) - 1);
-    const int unit = blockIdx.x >> C;
+    const int unit = (blockIdx.x >> C) + A.unit0;
     // the special-prime units (longest: they also run the fused inverse transforms) are scheduled first
     const int L = A.L;
     const int b = unit < A.B ? unit : (unit - A.B) / L, I = unit < A.B ? L : (unit - A.B) % L;
     const int ki = (I == L) ? A.K - 1 : I;
     const Mod m = T.mods[ki];
-    if (m.dp) ks_inner_body<LOGN, C, true>(T, A, m, b, I, ki, r);
-    else ks_inner_body<LOGN, C, false>(T, A, m, b, I, ki, r);
+    if (m.dp) ks_inner_body<LOGN, C, true, PAIRS>(T, A, m, b, I, ki, r);
+    else ks_inner_body<LOGN, C, false, PAIRS>(T, A, m, b, I, ki, r);
 }
 
 // Device form of a key-switching key, built once per upload from SEAL's [Ltop][2][K][N] array: every limb becomes

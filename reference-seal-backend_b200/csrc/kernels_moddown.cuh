@@ -86,8 +86,8 @@ __device__ __forceinline__ void moddown_body(const Tables &T, const ModDownArgs 
     auto load_t0 = [&]() { load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r); };
     if constexpr (C == 0) load_t0();
     auto split = [&](const u64 *src, auto pre) {
-        if constexpr (C == 0) load_fwd_split<LOGN>(x, src, c, r, tid, tw, m, pre, sm);
-        else load_fwd_split<LOGN>(x, src, c, r, tid, tw, m, pre, sm, load_t0);
+        if constexpr (C == 0) load_fwd_split<LOGN>(x, src, c, r, tid, tw, m, pre, sm);   // (limbs of four chunks: clusters of two, PAIRS)
+        else load_fwd_split<LOGN, false, true>(x, src, c, r, tid, tw, m, pre, sm, load_t0);
     };
     const u64 *bp = A.base + (size_t)b * A.base_ct_stride + (size_t)p * A.base_poly_stride + (size_t)j * N + off;
     const u64 *ap = A.addend[p] ? A.addend[p] + (size_t)b * A.add_ct_stride + (size_t)j * N + off : nullptr;

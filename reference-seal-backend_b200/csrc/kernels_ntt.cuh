@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::THREADS) k_ntt_fwd(Tables T, con
     u64 x[16];
     TwRegs<LOGN, 0> t0;
     load_tw_early<LOGN, 0, false>(t0, tw, tid, (1 << c) + r);
-    load_fwd_split<LOGN>(x, src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N, c, r, tid, tw, m, PreNone(), sm);
+    load_fwd_split<LOGN, false, true>(x, src + (size_t)(w / L) * src_outer + (size_t)(w % L) * T.N, c, r, tid, tw, m, PreNone(), sm);
     ntt_fwd_regs_split<LOGN>(x, sm, tw, m, tid, c, r, t0);
     u64 *out = dst + (size_t)(w / L) * dst_outer + (size_t)(w % L) * T.N + (size_t)r * NL;
     canon_all(x, m);

@@ -1,17 +1,35 @@
 // tu_ks.cu -- instantiations and launcher of the key-switch inner product k_ks_inner (K6 step 2).
+#include <stdlib.h>
+
 #include "launch.h"
 
 namespace b200he {
 
 void launch_ks_inner(const Geo &g, const Tables &T, const KsInnerArgs &A, size_t units)
 {
+    static const int split_min = []() { const char *e = getenv("B200HE_KS_SPLIT_MIN"); return e ? atoi(e) : 200; }();   // (tests set 1)
+    if (g.c == 2 && g.lognl == 13 && units > (size_t)A.B && A.B >= split_min) {
+        // special-prime units (0 .. B-1: forward transforms, inner product and the fused inverse transforms) in clusters of
+        // four; everything else in clusters of two (k_ks_inner, PAIRS).  Only for launches whose special-prime part fills the
+        // chip several times over on its own: the two launches run one after the other, and with B = 100 (MatMult Row) the
+        // tail of the first costs more than the second gains (measured: k_ks_inner 354 -> 383 ms split, C5 at B = 1024
+        // 160.6 -> 148.5 ms).
+        KsInnerArgs S = A, D = A;
+        S.unit0 = 0;
+        D.unit0 = (int)A.B;
+        B200HE_LAUNCH_CLUSTER((k_ks_inner<13, 2, false>), (unsigned)((size_t)A.B << 2), NttCfg<13>::THREADS, KsCfg<13>::SMEM_BYTES, g.stream, 4u, T, S);
+        B200HE_LAUNCH_CLUSTER((k_ks_inner<13, 2, true>), (unsigned)((units - (size_t)A.B) << 2), NttCfg<13>::THREADS, KsCfg<13>::SMEM_BYTES, g.stream, 2u, T, D);
+        return;
+    }
     KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ks_inner<LG, CC>), (unsigned)(units << g.c), NttCfg<LG>::THREADS, KsCfg<LG>::SMEM_BYTES, g.stream, 1u << g.c, T, A));
 }
 
 template <int LG, int CC> static int attrs()
 {
 #ifndef B200HE_EMU
-    return (int)cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES);
+    int rc = (int)cudaFuncSetAttribute(k_ks_inner<LG, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES);
+    if (CC == 2 && !rc) rc = (int)cudaFuncSetAttribute(k_ks_inner<LG, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<LG>::SMEM_BYTES);
+    return rc;
 #else
     return 0;
 #endif

@@ -9,7 +9,9 @@ void launch_moddown_kind(const Geo &g, int kind, const Tables &T, const ModDownA
     const unsigned grid = (unsigned)(units << g.c);
     // clusters of two exchange nothing in the forward direction (load_fwd_split computes their cross stage from global
     // memory): the two CTAs of a limb are launched as ordinary CTAs, free to land on any SM
-    const unsigned cl = g.c == 1 ? 1u : 1u << g.c;
+    // limbs of four chunks: clusters of TWO (the stage that pairs chunk r with r ^ 2 also comes from global memory, the
+    // other one is exchanged inside the pair; clusters of four would keep only 132 of the 148 SMs busy)
+    const unsigned cl = g.c == 1 ? 1u : g.c == 2 ? 2u : 1u;
     if (kind == KIND_INT) {
         KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_moddown<LG, CC>), grid, NttCfg<LG>::THREADS, (D.gal ? ModDownCfg<LG>::SMEM_BYTES_GAL : ModDownCfg<LG>::SMEM_BYTES), g.stream, cl, T, D));
     } else if (kind == KIND_DP) {

@@ -12,7 +12,7 @@ void launch_ntt_fwd(const Geo &g, const Tables &T, const u64 *src, u64 *dst, siz
         return;
     }
     KERNEL_DISPATCH(g, B200HE_LAUNCH_CLUSTER((k_ntt_fwd<LG, CC>), (unsigned)(nlimbs << g.c), NttCfg<LG>::THREADS, NttCfg<LG>::SMEM_BYTES, g.stream,
-                                             (g.c == 1 ? 1u : 1u << g.c) /* forward, clusters of two: no exchange (load_fwd_split) */, T,
+                                             (g.c == 2 ? 2u : 1u) /* forward: limbs of two chunks exchange nothing, limbs of four chunks exchange inside pairs (load_fwd_split) */, T,
                                              src, dst, src_outer, dst_outer, L, mod_base));
 }
 

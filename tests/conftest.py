@@ -10,6 +10,11 @@ sys.path.insert(0, os.path.join(ROOT, "reference-seal-backend_b200"))
 sys.path.insert(0, ROOT)
 
 
+# the key-switch inner product of four-chunk limbs runs as two launches only for large batches (tu_ks.cu); the tests' batches
+# are small, so the threshold is lowered for every library and plugin process the tests start
+os.environ.setdefault("B200HE_KS_SPLIT_MIN", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
