@@ -12,12 +12,13 @@
 //
 // CTA shape.  Every NTT-bearing kernel runs CTAs of N_loc/16 threads (512 for N >= 8192) that own a local transform of
 // N_loc = min(N, 8192) coefficients: 64 KiB of shared memory, 16 coefficients per thread in registers.  For N = 16384 /
-// 32768 a limb belongs to a group of 2 / 4 CTAs; CTA r owns chunk r.  In a cluster of 4 the two transform stages that
-// span chunks run as one radix-4 butterfly per offset on values exchanged through distributed shared memory (cross_fwd /
-// cross_inv below): no butterfly is computed twice and no second kernel finishes a split inverse.  A group of 2 does the
-// same for its inverse cross stage; in the forward direction each of the two CTAs reads its sibling's chunk from global
-// memory (L2) and computes the single cross stage for itself -- half a butterfly per coefficient costs less than the
-// DSMEM round trip and the two cluster barriers (load_fwd_split; measured).
+// 32768 a limb belongs to a group of 2 / 4 CTAs; CTA r owns chunk r.  INVERSE transforms exchange the one or two stages that
+// span chunks through distributed shared memory inside a cluster of 2 / 4 (cross_inv: one radix-2/4 butterfly per offset, no
+// butterfly computed twice, no second kernel).  In the FORWARD direction a stage that pairs two chunks is cheaper to compute
+// from global memory than to exchange: a group of 2 reads its sibling's chunk (L2) and exchanges nothing; a group of 4 does
+// that for its first cross stage and exchanges the second inside clusters of TWO (load_fwd_split, cross_fwd_pair) -- clusters
+// of four keep only 132 of the 148 SMs busy.  k_ks_inner's special-prime units, which also run inverse transforms, still use
+// the four-CTA exchange of cross_fwd.  (Measured)
 #pragma once
 #include "ntt_core.cuh"
 #ifndef B200HE_EMU
