@@ -147,6 +147,8 @@ struct b200he_ctx {
     // copy that used it
     void *stage_buf[2] = { nullptr, nullptr };
     cudaEvent_t stage_ev[2] = { nullptr, nullptr };
+    cudaStream_t aux = nullptr;                     // side stream of launch pairs that may overlap (launch.h Geo)
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     size_t stage_bytes = 0;
 };
 
@@ -206,7 +208,7 @@ static inline void prof_post(b200he_ctx *c)
         CALL;                \
         prof_post(ctx);      \
     } while (0)
-static inline Geo geo(const b200he_ctx *c) { return Geo{ c->lognl, c->c, c->stream }; }
+static inline Geo geo(const b200he_ctx *c) { return Geo{ c->lognl, c->c, c->stream, c->aux, c->aux_fork, c->aux_join }; }
 
 static inline unsigned blocks_for(size_t threads, unsigned block = 256) { return (unsigned)((threads + block - 1) / block); }
 
@@ -411,6 +413,14 @@ extern "C" int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint6
 #ifndef B200HE_EMU
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("ctx_create: stream"));
     c->own_stream = true;
+    {
+        const char *e = getenv("B200HE_KS_OVERLAP");
+        if ((!e || atoi(e) != 0) && c->c == 2) {   // only limbs of four chunks have a launch pair to overlap
+            if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming) != cudaSuccess)
+                return bail(fail("ctx_create: side stream"));
+        }
+    }
 #endif
     if (int rc = set_smem_attrs(c)) return bail(rc);
     // pinned staging for load()/store() (page-locking 64 MB takes tens of milliseconds: not inside the first load)
@@ -451,6 +461,9 @@ extern "C" void b200he_ctx_destroy(b200he_ctx *c)
     }
 #ifndef B200HE_EMU
     if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
+    if (c->aux_join) cudaEventDestroy(c->aux_join);
 #endif
     delete c;
 }

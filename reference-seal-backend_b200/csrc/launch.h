@@ -37,6 +37,10 @@ namespace b200he {
 struct Geo {
     int lognl, c;
     cudaStream_t stream;
+    // side stream + fork / join events of the context (nullptr: none): k_ks_inner's two launches for four-chunk limbs run next
+    // to each other, so that the clusters of two of one fill the SMs that the clusters of four of the other cannot use
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
 };
 
 // dispatch on the CTA-local transform size LG (unsplit limbs)
