@@ -48,7 +48,9 @@ const char *b200he_version(void);
 int b200he_ctx_create(int scheme, uint32_t N, uint32_t K, const uint64_t *moduli, const uint64_t *psi,
                       uint64_t plain_modulus, int device, b200he_ctx **out);
 void b200he_ctx_destroy(b200he_ctx *ctx);
-/* run on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream */
+/* run on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream.  Every call is ordered on that
+ * stream; contexts with N = 32768 also own a side stream for one pair of key-switch launches, forked from and joined back into
+ * the caller's stream with events inside the call, so the ordering the caller sees does not change. */
 int b200he_ctx_set_stream(b200he_ctx *ctx, void *cuda_stream);
 int b200he_ctx_sync(b200he_ctx *ctx);
 /* scratch budget per evaluator call in bytes (large batches are processed in chunks) */
